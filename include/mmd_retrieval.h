@@ -1,0 +1,133 @@
+/*
+ * mmd_retrieval.h -- C ABI of libmmd.so, the B200-native (sm_100a) evidence-retrieval hot path.
+ *
+ * This is the drop-in boundary for the ONE path this repo accelerates: the embedding-similarity
+ * evidence retrieval of sakdag/multimodal-misinformation-detection (paths below are relative to the
+ * reference checkout):
+ *
+ *   src/evidence/im2im_retrieval.py:38-42     ImageSimilarity.similarity  (pairwise cosine, eps=1e-6)
+ *   src/evidence/im2im_retrieval.py:80-106    ImageCorpus.retrieve_similar_images (score all, sort, dedupe)
+ *   src/evidence/text2text_retrieval.py:56-64 util.semantic_search(q, corpus, top_k=...)  (third-party
+ *                                             sentence-transformers==3.3.1: normalise -> mm -> topk -> heap)
+ *   src/evidence/experiment_text.py:25-33, src/evidence/experiment_image.py:25-33   same, in the eval loops
+ *
+ * The reference is pure Python and has no FFI of its own; this header is what a ctypes binding on the
+ * reference side would load (see INTEGRATION.md for that stub).  All pointers are DEVICE pointers unless
+ * the name ends in _host; the caller owns every buffer; the library allocates nothing persistent except
+ * a small per-device status word.  Every call is asynchronous on `stream` (a cudaStream_t passed as
+ * void*), returns 0 on success or a negative mmd_status, and never falls back to the CPU: on a device
+ * that is not sm_100 the compute entry points return MMD_ERR_DEVICE.
+ *
+ * Contract of the path: (query embeddings [Q,D], corpus embeddings [N,D], K) -> (scores f32 [Q,K] sorted
+ * descending, indices i32 [Q,K] = 0-based corpus rows).  Ties are ordered by ascending corpus row.
+ * Slots beyond min(K,N) hold score = -inf and index = -1.
+ */
+#ifndef MMD_RETRIEVAL_H_
+#define MMD_RETRIEVAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MMD_API __attribute__((visibility("default")))
+#else
+#define MMD_API
+#endif
+
+typedef enum mmd_status {
+  MMD_OK = 0,
+  MMD_ERR_ARG = -1,       /* bad argument (null pointer, non-positive size, unsupported K, misalignment) */
+  MMD_ERR_DEVICE = -2,    /* no CUDA device, or device is not compute capability 10.x */
+  MMD_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed; see mmd_last_error() */
+  MMD_ERR_WORKSPACE = -4, /* workspace too small; call mmd_topk_workspace_bytes() */
+  MMD_ERR_KERNEL = -5     /* a kernel reported a pipeline fault through the device status word */
+} mmd_status;
+
+/* dtype of caller-side embeddings (what the reference stores: fp32 image features
+ * im2im_retrieval.py:29-36, fp16 text embeddings text2text_retrieval.py:44,53). */
+typedef enum mmd_src_dtype { MMD_SRC_F32 = 0, MMD_SRC_F16 = 1, MMD_SRC_BF16 = 2 } mmd_src_dtype;
+
+/* operand format of the prepared (normalised, cast) rows the tensor-core contraction reads. */
+typedef enum mmd_op_dtype {
+  MMD_OP_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)                        */
+  MMD_OP_F16 = 1,    /* fp16 operands, fp32 accumulate (tcgen05 kind::f16)                        */
+  MMD_OP_E4M3 = 2,   /* fp8 e4m3 operands scaled by 2^8, fp32 accumulate (tcgen05 kind::f8f6f4)   */
+  MMD_OP_BF16X3 = 3  /* fp32-accurate: every value split into 3 bf16 limbs, 6 cross terms laid
+                        out along K, fp32 accumulate (the "fp32" configuration of the path)      */
+} mmd_op_dtype;
+
+typedef enum mmd_side { MMD_SIDE_QUERY = 0, MMD_SIDE_CORPUS = 1 } mmd_side;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+MMD_API int mmd_abi_version(void);
+/* Human-readable text of the last failure on the calling thread ("" if none). */
+MMD_API const char* mmd_last_error(void);
+/* 0 if the current CUDA device can run the path (compute capability 10.x), else MMD_ERR_DEVICE. */
+MMD_API int mmd_device_check(void);
+
+/* ---- K1: fused normalise-and-cast ---------------------------------------------------------- */
+/* Layout of prepared rows for (op_dtype, dim): *kdim = length of the contraction axis in operand
+ * elements (dim padded to 16 bytes; x6 for BF16X3), *row_bytes = pitch of one prepared row. */
+MMD_API int mmd_prepared_layout(int op_dtype, int dim, int64_t* kdim, int64_t* row_bytes);
+
+/* dst[r,:] = cast(src[r,:] * (normalize ? 1/max(||src[r,:]||_2, eps) : 1))  for r in [0,rows)
+ * (F.normalize semantics, sentence_transformers.util.cos_sim; nn.CosineSimilarity per-norm clamp,
+ * im2im_retrieval.py:40).  inv_norm (nullable) receives the fp32 row multipliers.  src rows are
+ * src_row_stride elements apart.  side selects the limb order for MMD_OP_BF16X3. */
+MMD_API int mmd_normalize_cast(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride,
+                       int normalize, float eps, int op_dtype, int side, void* dst, float* inv_norm,
+                       void* stream);
+
+/* ---- K2+K3: tensor-core score contraction with fused top-K ---------------------------------- */
+/* Largest K the fused selection supports. */
+MMD_API int mmd_topk_max_k(void);
+/* Bytes of scratch mmd_topk_scores needs for this problem. */
+MMD_API size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op_dtype, int k);
+
+/* q_prep [Q rows], c_prep [N rows]: prepared by mmd_normalize_cast with the same op_dtype / dim.
+ * out_scores f32 [Q,k] descending, out_idx i32 [Q,k] = corpus row + idx_offset.  The Q x N score
+ * matrix is never written to memory. */
+MMD_API int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
+                    int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Same contraction, dense output scores f32 [Q, ld_scores] (small shapes: pairwise similarity,
+ * tests, custom post-processing). */
+MMD_API int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
+                     float* out_scores, int64_t ld_scores, void* stream);
+
+/* ---- K3b/K4: merge of partial top-K lists ---------------------------------------------------- */
+/* scores/idx: [parts, Q, k_in] (e.g. the all-gathered per-rank lists of a row-sharded corpus);
+ * out: [Q, k_out] best by (score desc, idx asc).  parts*k_in <= 4096. */
+MMD_API int mmd_topk_merge(const float* scores, const int32_t* idx, int parts, int64_t Q, int k_in, int k_out,
+                   float* out_scores, int32_t* out_idx, void* stream);
+
+/* ---- K5: exact re-score of the selected candidates ------------------------------------------ */
+/* For each query q and candidate j < k_in with cand_idx[q,j] >= 0 :
+ *   s = (sum_i q_src[q,i] * c_src[cand_idx[q,j] - idx_offset, i]) * q_inv[q] * c_inv[row]   (fp32)
+ * then the k_out best by (s desc, idx asc) are written.  q_inv / c_inv may be NULL (= 1). */
+MMD_API int mmd_rescore(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
+                int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
+                const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, float* out_scores,
+                int32_t* out_idx, void* stream);
+
+/* ---- measurement hooks ------------------------------------------------------------------------ */
+/* While enabled, every fused contraction launch of mmd_topk_scores is bracketed by CUDA events on its own
+ * stream (up to 512 launches are kept).  mmd_profile_collect synchronises those events, writes up to `cap`
+ * durations in milliseconds (oldest first), clears the list and returns how many it wrote. */
+MMD_API int mmd_profile_enable(int on);
+MMD_API int mmd_profile_collect(float* ms_host, int cap);
+
+/* Launch counter: number of kernels this library has launched in this process (bench evidence). */
+MMD_API int64_t mmd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMD_RETRIEVAL_H_ */

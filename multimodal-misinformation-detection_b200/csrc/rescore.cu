@@ -1,0 +1,173 @@
+// K5: exact fp32 re-score of the few candidates the low-precision tensor-core pass selected.
+//
+// The bf16 / fp8 contraction decides WHICH corpus rows are candidates (over-fetched to k_in > k_out); this
+// kernel recomputes their cosine from the caller's original embeddings in fp32 -- the arithmetic of the
+// reference (F.normalize + mm in sentence_transformers.util.cos_sim; nn.CosineSimilarity in
+// src/evidence/im2im_retrieval.py:38-42) -- and re-ranks.  Returned scores therefore agree with the fp32
+// reference to rounding, and the order inside the returned list is the fp32 order.
+//
+// One 128-thread block per query: warps stride over candidates, each computing one D-long dot product
+// with 128-bit gathered loads (HBM/L2-bound gather: Q * k_in * D * sizeof(src) bytes), then a rank-by-
+// counting pass orders the <= 1024 candidates.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace mmd {
+namespace {
+
+constexpr int kMaxCand = 1024;
+
+template <typename T>
+__device__ __forceinline__ float cvt(T v);
+template <>
+__device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float cvt<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float cvt<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+struct Vec {
+  static constexpr int kElems = 16 / sizeof(T);
+};
+
+template <typename TQ, typename TC>
+__device__ __forceinline__ float warp_dot(const TQ* __restrict__ a, const TC* __restrict__ b, int dim, int lane,
+                                          bool vec_ok) {
+  float acc = 0.0f;
+  if (vec_ok) {
+    // 8 elements per lane per step; both rows 16-byte aligned, dim % 8 == 0
+    for (int i = lane * 8; i < dim; i += 256) {
+      float x[8], y[8];
+      if constexpr (sizeof(TQ) == 4) {
+        const float4 u = *reinterpret_cast<const float4*>(a + i), w = *reinterpret_cast<const float4*>(a + i + 4);
+        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+        const TQ* p = reinterpret_cast<const TQ*>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = cvt<TQ>(p[j]);
+      }
+      if constexpr (sizeof(TC) == 4) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(b + i)), w = __ldg(reinterpret_cast<const float4*>(b + i + 4));
+        y[0] = u.x; y[1] = u.y; y[2] = u.z; y[3] = u.w; y[4] = w.x; y[5] = w.y; y[6] = w.z; y[7] = w.w;
+      } else {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(b + i));
+        const TC* p = reinterpret_cast<const TC*>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = cvt<TC>(p[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(x[j], y[j], acc);
+    }
+  } else {
+    for (int i = lane; i < dim; i += 32) acc = fmaf(cvt<TQ>(a[i]), cvt<TC>(b[i]), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+template <typename TQ, typename TC>
+__global__ void __launch_bounds__(128)
+rescore_kernel(const TQ* __restrict__ q_src, int64_t q_stride, const float* __restrict__ q_inv,
+               const TC* __restrict__ c_src, int64_t c_stride, const float* __restrict__ c_inv, int64_t N, int dim,
+               const int32_t* __restrict__ cand_idx, int k_in, int64_t idx_offset, int k_out,
+               float* __restrict__ out_s, int32_t* __restrict__ out_i, bool vec_ok) {
+  __shared__ uint64_t keys[kMaxCand];
+  const int64_t q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TQ* qrow = q_src + q * q_stride;
+  const float qi = q_inv != nullptr ? q_inv[q] : 1.0f;
+  for (int j = warp; j < k_in; j += 4) {
+    const int32_t gi = cand_idx[q * k_in + j];
+    uint64_t key = 0ull;
+    const int64_t row = static_cast<int64_t>(gi) - idx_offset;
+    if (gi >= 0 && row >= 0 && row < N) {
+      const float d = warp_dot<TQ, TC>(qrow, c_src + row * c_stride, dim, lane, vec_ok);
+      const float ci = c_inv != nullptr ? c_inv[row] : 1.0f;
+      key = make_key(d * qi * ci, static_cast<uint32_t>(gi));
+    }
+    if (lane == 0) keys[j] = key;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k_in; j += 128) {
+    const uint64_t mine = keys[j];
+    int rank = 0;
+    for (int t = 0; t < k_in; ++t) {
+      const uint64_t o = keys[t];
+      rank += (o > mine) || (o == mine && t < j);
+    }
+    if (rank < k_out) {
+      if (mine == 0ull) {
+        out_s[q * k_out + rank] = __int_as_float(0xff800000);
+        out_i[q * k_out + rank] = -1;
+      } else {
+        out_s[q * k_out + rank] = key_score(mine);
+        out_i[q * k_out + rank] = static_cast<int32_t>(key_row(mine));
+      }
+    }
+  }
+  for (int i = k_in + threadIdx.x; i < k_out; i += 128) {
+    out_s[q * k_out + i] = __int_as_float(0xff800000);
+    out_i[q * k_out + i] = -1;
+  }
+}
+
+template <typename TQ, typename TC>
+int launch(const void* q_src, int64_t q_stride, const float* q_inv, const void* c_src, int64_t c_stride,
+           const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in, int64_t idx_offset,
+           int k_out, float* out_s, int32_t* out_i, cudaStream_t stream) {
+  const bool vec_ok = dim % 8 == 0 && reinterpret_cast<uintptr_t>(q_src) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(c_src) % 16 == 0 && (q_stride * sizeof(TQ)) % 16 == 0 &&
+                      (c_stride * sizeof(TC)) % 16 == 0;
+  rescore_kernel<TQ, TC><<<static_cast<unsigned>(Q), 128, 0, stream>>>(
+      static_cast<const TQ*>(q_src), q_stride, q_inv, static_cast<const TC*>(c_src), c_stride, c_inv, N, dim, cand_idx,
+      k_in, idx_offset, k_out, out_s, out_i, vec_ok);
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
+}
+
+template <typename TQ>
+int dispatch_c(int c_dtype, const void* q_src, int64_t q_stride, const float* q_inv, const void* c_src, int64_t c_stride,
+               const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in, int64_t idx_offset,
+               int k_out, float* out_s, int32_t* out_i, cudaStream_t stream) {
+  switch (c_dtype) {
+    case MMD_SRC_F32: return launch<TQ, float>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
+    case MMD_SRC_F16: return launch<TQ, __half>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
+    case MMD_SRC_BF16: return launch<TQ, __nv_bfloat16>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
+  }
+  set_last_error("mmd_rescore: unknown c_dtype %d", c_dtype);
+  return MMD_ERR_ARG;
+}
+
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_rescore(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
+                           int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
+                           const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, float* out_scores,
+                           int32_t* out_idx, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k_in > 0 && k_out > 0, "mmd_rescore: Q=%lld N=%lld dim=%d k_in=%d k_out=%d",
+              (long long)Q, (long long)N, dim, k_in, k_out);
+  MMD_REQUIRE(k_in <= kMaxCand, "mmd_rescore: k_in %d exceeds %d", k_in, kMaxCand);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(q_src != nullptr && cand_idx != nullptr && out_scores != nullptr && out_idx != nullptr,
+              "mmd_rescore: null buffer");
+  MMD_REQUIRE(c_src != nullptr || N == 0, "mmd_rescore: null corpus");
+  MMD_REQUIRE(q_stride >= dim && (c_stride >= dim || N == 0), "mmd_rescore: row stride smaller than dim");
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (q_dtype) {
+    case MMD_SRC_F32: return dispatch_c<float>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
+    case MMD_SRC_F16: return dispatch_c<__half>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
+    case MMD_SRC_BF16: return dispatch_c<__nv_bfloat16>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
+  }
+  set_last_error("mmd_rescore: unknown q_dtype %d", q_dtype);
+  return MMD_ERR_ARG;
+}

@@ -1,0 +1,691 @@
+// K2+K3: query x corpus score contraction on tcgen05 tensor cores with the top-K selection fused
+// into the TMEM epilogue, so the Q x N score matrix never reaches HBM.
+//
+// Reference arithmetic this replaces (paths relative to the reference checkout):
+//   torch.mm(a_norm, b_norm.T) + torch.topk + per-query heapq merge inside
+//     sentence_transformers.util.semantic_search   (call sites src/evidence/text2text_retrieval.py:56-64,
+//                                                   src/evidence/experiment_text.py:25-33)
+//   the O(N) python loop + full sort of               src/evidence/im2im_retrieval.py:84-92,
+//                                                     src/evidence/experiment_image.py:25-33
+//
+// Shape of the kernel (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0 (one lane)  TMA producer: {128 queries x 128 B} and {256 corpus rows x 128 B} boxes, 128B swizzle,
+//                      multi-stage ring of mbarriers.
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma 128x256x(32 B) into one of two 256-column TMEM accumulators.
+//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> query row.  A register
+//                      threshold (the row's current K-th best) filters 32 scores with a max tree and one
+//                      vote; survivors are appended to a per-row candidate buffer in shared memory which
+//                      the warp compacts with a shuffle bitonic sort when it fills.
+// Work decomposition: unit = (128-query tile, strip of T corpus tiles), query tile fastest so that the
+// CTAs running at the same time read the same corpus rows (L2 reuse; HBM sees the corpus ~once).
+// Every unit leaves a sorted K-list per query; topk_merge.cu folds the strips together.
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmd {
+
+int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
+                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+
+namespace {
+
+constexpr int kTileM = 128;          // queries per tile  (UMMA M, TMEM lanes)
+constexpr int kTileN = 256;          // corpus rows per tile (UMMA N, TMEM columns)
+constexpr int kBlockKBytes = 128;    // one swizzle atom along K per stage
+constexpr int kABytes = kTileM * kBlockKBytes;   // 16 KB
+constexpr int kBBytes = kTileN * kBlockKBytes;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;   // 48 KB
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
+constexpr int kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
+
+struct FusedParams {
+  int64_t Q, N;
+  int kblocks;           // ceil(row_bytes / 128)
+  int n_m, n_n;          // query tiles, corpus tiles
+  int tiles_per_strip;   // T
+  int n_strips;          // S
+  int n_units;           // n_m * S
+  int kprime;            // list length kept per (query, strip)
+  int stages;
+  uint64_t* partial;     // [Q][S][kprime] keys
+  float* dense;          // dense mode: [Q][ldd] scores
+  int64_t ldd;
+  float out_scale;       // dense mode: multiplier applied to the accumulators
+  DeviceStatus* status;
+};
+
+struct SmemLayout {
+  uint32_t stage_off;    // stages x {A,B}
+  uint32_t keys_off;     // 4 warps x CAP x 32 keys
+  uint32_t bars_off;     // full[8], empty[8], tmem_full[2], tmem_empty[2]
+  uint32_t tmem_ptr_off;
+  uint32_t total;        // including 1024 B of alignment slack
+};
+__host__ __device__ inline SmemLayout smem_layout(int stages, int cap) {
+  SmemLayout l;
+  l.stage_off = 0;
+  l.keys_off = stages * kStageBytes;
+  l.bars_off = l.keys_off + cap * 32 * 4 * 8;
+  l.tmem_ptr_off = l.bars_off + (2 * kMaxStages + 4) * 8;
+  l.total = l.tmem_ptr_off + 16 + 1024;
+  return l;
+}
+
+// ---------------------------------------------------------------- warp-cooperative list maintenance
+// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + ((r + slot) & 31)]: conflict-free both
+// when the 32 row-owner lanes append and when the whole warp reads one row.
+__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + ((r + slot) & 31); }
+
+template <int E>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t (&k)[E], int lane) {
+  // element index i = e * 32 + lane over 32 * E elements; result descending in i.
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int es = stride >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & es) == 0) {
+            const int i_low = e * 32 + lane;
+            const bool desc = (i_low & size) == 0;
+            const uint64_t a = k[e], b = k[e | es];
+            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+            k[e] = desc ? mx : mn;
+            k[e | es] = desc ? mn : mx;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int i = e * 32 + lane;
+          const uint64_t other = __shfl_xor_sync(kFullMask, k[e], stride);
+          const bool lower = (lane & stride) == 0;
+          const bool desc = (i & size) == 0;
+          const bool take_max = (lower == desc);
+          const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
+          k[e] = take_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+// Sort the candidate buffers of the rows named in `mask`; keep the best `kprime`.
+//   FINAL = false : write the survivors back, refresh the owner's count and threshold.
+//   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
+template <int CAP, bool FINAL>
+__device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int& cnt, float& thr,
+                                             uint64_t* out_rows, int64_t out_row_stride) {
+  constexpr int E = CAP / 32;
+  __syncwarp();
+  while (mask) {
+    const int r = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int n = __shfl_sync(kFullMask, cnt, r);
+    uint64_t k[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      k[e] = (i < n) ? wkeys[key_slot_index(i, r)] : 0ull;
+    }
+    bitonic_sort_desc<E>(k, lane);
+    if constexpr (!FINAL) {
+      const int keep = n < kprime ? n : kprime;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        if (i < keep) wkeys[key_slot_index(i, r)] = k[e];
+      }
+      const int last = kprime - 1;
+      uint64_t kk = k[0];
+#pragma unroll
+      for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[e] : kk;
+      kk = __shfl_sync(kFullMask, kk, last & 31);
+      if (lane == r) {
+        cnt = keep;
+        if (n >= kprime) thr = key_score(kk);
+      }
+    } else {
+      uint64_t* out = out_rows + static_cast<int64_t>(r) * out_row_stride;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        if (i < kprime) out[i] = k[e];   // empty slots are key 0
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int CAP, bool kF8, bool kDense>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                        const FusedParams p, const uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024-byte alignment.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int T = p.tiles_per_strip;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int m_tile = u % p.n_m;
+        const int strip = u / p.n_m;
+        const int t0 = strip * T;
+        const int t1 = min(t0 + T, p.n_n);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            uint8_t* sa = smem + L.stage_off + stage * kStageBytes;
+            const int kelem = kb * (kF8 ? kBlockKBytes : kBlockKBytes / 2);
+            tma_load_2d(sa, &tmap_q, &full_bar[stage], kelem, m_tile * kTileM, kEvictLast);
+            tma_load_2d(sa + kABytes, &tmap_c, &full_bar[stage], kelem, t * kTileN, kEvictNormal);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int strip = u / p.n_m;
+        const int t0 = strip * T;
+        const int t1 = min(t0 + T, p.n_n);
+        for (int t = t0; t < t1; ++t, ++it) {
+          const uint32_t buf = it & 1;
+          mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, p.status, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kTileN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase, p.status, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + L.stage_off + stage * kStageBytes);
+            const uint64_t adesc = make_smem_desc_sw128(sa);
+            const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockKBytes / 32; ++k) {
+              // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma<1, kF8>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[buf]);         // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (2..5)
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(warp - 2) * (CAP * 32);
+    const float kNegInf = __int_as_float(0xff800000);
+    const float kPosInf = __int_as_float(0x7f800000);
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int m_tile = u % p.n_m;
+      const int strip = u / p.n_m;
+      const int t0 = strip * T;
+      const int t1 = min(t0 + T, p.n_n);
+      const int64_t qrow = static_cast<int64_t>(m_tile) * kTileM + row_in_tile;
+      const bool valid = qrow < p.Q;
+      float thr = valid ? kNegInf : kPosInf;
+      int cnt = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tmem_full[buf], (it >> 1) & 1, p.status, 4);
+        tc_fence_after();
+        const int64_t col_tile = static_cast<int64_t>(t) * kTileN;
+        const bool edge = col_tile + kTileN > p.N;
+#pragma unroll 1
+        for (int c = 0; c < kTileN / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+          tmem_ld_wait();
+          if (c == kTileN / 32 - 1) {
+            // the whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+          }
+          const int64_t col0 = col_tile + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if constexpr (kDense) {
+            if (valid) {
+              float* out = p.dense + qrow * p.ldd + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) out[j] = v[j] * p.out_scale;
+            }
+          } else {
+            if (edge) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= p.N) v[j] = kNegInf;
+            }
+            float m = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+            if (__any_sync(kFullMask, m > thr)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
+                if (need) compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float x = v[g * 8 + j];
+                  if (x > thr) {
+                    wkeys[key_slot_index(cnt, lane)] = make_key(x, static_cast<uint32_t>(col0 + g * 8 + j));
+                    ++cnt;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if constexpr (!kDense) {
+        // unit done: emit the sorted K-list of every valid row of this warp
+        const uint32_t vmask = __ballot_sync(kFullMask, valid);
+        const int64_t row0 = static_cast<int64_t>(m_tile) * kTileM + quarter * 32;
+        uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
+        compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
+                                static_cast<int64_t>(p.n_strips) * p.kprime);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+// Tensor map over prepared rows: dims {kdim, rows}, box {128 B of K, box_rows}, 128B swizzle, zero OOB fill.
+int make_rows_tensor_map(CUtensorMap* tm, const void* base, int op_dtype, int64_t rows, const PreparedLayout& lay,
+                         int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available from the driver");
+    return MMD_ERR_CUDA;
+  }
+  CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (op_dtype == MMD_OP_F16) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  if (op_dtype == MMD_OP_E4M3) dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(lay.kdim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(lay.row_bytes)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockKBytes / lay.elem_bytes), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld kdim=%lld pitch=%lld)", (int)r,
+                   (long long)rows, (long long)lay.kdim, (long long)lay.row_bytes);
+    return MMD_ERR_CUDA;
+  }
+  return MMD_OK;
+}
+
+int cap_for_k(int kprime) {
+  if (kprime <= 24) return 32;
+  if (kprime <= 56) return 64;
+  if (kprime <= 120) return 128;
+  return 0;
+}
+
+struct Schedule {
+  int n_m, n_n, T, S, n_units, grid;
+};
+
+// Pick the strip length: static round-robin of units over `sms` CTAs; minimise the busiest CTA's tile
+// count, then prefer fewer strips (fewer list restarts and a cheaper merge).
+Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms) {
+  Schedule s{};
+  s.n_m = static_cast<int>(ceil_div(Q, kTileM));
+  s.n_n = static_cast<int>(ceil_div(N, kTileN));
+  const int max_parts = kprime > 0 ? 4096 / kprime : 4096;
+  int s_max = s.n_n < max_parts ? s.n_n : max_parts;
+  if (s_max > 1024) s_max = 1024;
+  if (s_max < 1) s_max = 1;
+  int64_t best_load = -1;
+  int best_S = 1, best_T = s.n_n;
+  // first pass: find the minimal busiest-CTA load
+  struct Cand { int S, T; int64_t load; };
+  Cand cands[1024];
+  int nc = 0;
+  int last_T = -1;
+  for (int S = 1; S <= s_max; ++S) {
+    const int T = static_cast<int>(ceil_div(s.n_n, S));
+    if (T == last_T) continue;
+    last_T = T;
+    const int S_eff = static_cast<int>(ceil_div(s.n_n, T));
+    const int64_t units = static_cast<int64_t>(s.n_m) * S_eff;
+    const int G = static_cast<int>(units < sms ? units : sms);
+    const int T_last = s.n_n - (S_eff - 1) * T;
+    int64_t worst = 0;
+    for (int c = 0; c < G; ++c) {
+      const int64_t cnt = (units - 1 - c) / G + 1;
+      // units of CTA c that lie in the last strip: u in [units - n_m, units), u % G == c
+      const int64_t lo = units - s.n_m;
+      int64_t first = lo + ((c - lo % G) % G + G) % G;
+      const int64_t in_last = first < units ? (units - 1 - first) / G + 1 : 0;
+      const int64_t load = (cnt - in_last) * T + in_last * T_last;
+      if (load > worst) worst = load;
+    }
+    cands[nc++] = {S_eff, T, worst};
+    if (best_load < 0 || worst < best_load) best_load = worst;
+  }
+  for (int i = 0; i < nc; ++i) {
+    if (cands[i].load * 100 <= best_load * 102) {   // within 2% of the best balance: take the fewest strips
+      best_S = cands[i].S;
+      best_T = cands[i].T;
+      break;
+    }
+  }
+  s.S = best_S;
+  s.T = best_T;
+  s.n_units = s.n_m * s.S;
+  s.grid = s.n_units < sms ? s.n_units : sms;
+  return s;
+}
+
+}  // namespace
+
+// The status word lives in mapped pinned host memory so that the host can still read which wait
+// timed out after the watchdog trapped the context.
+static DeviceStatus* g_status_host = nullptr;
+DeviceStatus* device_status_word() {
+  static DeviceStatus* dev_ptr = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (dev_ptr == nullptr) {
+    DeviceStatus* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(DeviceStatus), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    h->code = 0; h->site = 0; h->block = 0; h->extra = 0;
+    DeviceStatus* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+    g_status_host = h;
+    dev_ptr = d;
+  }
+  return dev_ptr;
+}
+const DeviceStatus* host_status_word() { return g_status_host; }
+
+namespace {
+
+// Optional event bracketing of the fused launches (mmd_profile_enable / mmd_profile_collect).
+struct Profile {
+  std::mutex mu;
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+} g_profile;
+constexpr size_t kMaxProfiled = 512;
+
+template <int CAP, bool kF8, bool kDense>
+int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams& p, uint32_t idesc, int grid,
+                 cudaStream_t stream) {
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP);
+  auto kern = fused_score_topk_kernel<CAP, kF8, kDense>;
+  static bool attr_set = false;   // one per template instantiation
+  if (!attr_set) {
+    MMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool profiled = false;
+  {
+    std::lock_guard<std::mutex> g(g_profile.mu);
+    if (g_profile.on && !kDense && g_profile.events.size() < kMaxProfiled) {
+      if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) profiled = true;
+    }
+  }
+  if (profiled) cudaEventRecord(e0, stream);
+  kern<<<grid, kThreads, L.total, stream>>>(tq, tc, p, idesc);
+  if (profiled) {
+    cudaEventRecord(e1, stream);
+    std::lock_guard<std::mutex> g(g_profile.mu);
+    g_profile.events.emplace_back(e0, e1);
+  }
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
+}
+
+int stages_for(int cap) {
+  for (int st = kMaxStages; st >= 2; --st)
+    if (smem_layout(st, cap).total <= static_cast<uint32_t>(kMaxSmem)) return st;
+  return 0;
+}
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+uint32_t idesc_for(int op_dtype) {
+  // kind::f16: 0 = f16, 1 = bf16 ; kind::f8f6f4: 0 = e4m3
+  const uint32_t fmt = (op_dtype == MMD_OP_BF16 || op_dtype == MMD_OP_BF16X3) ? 1u : 0u;
+  return make_idesc(fmt, kTileM, kTileN);
+}
+
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_topk_max_k(void) { return 120; }
+
+extern "C" int mmd_profile_enable(int on) {
+  std::lock_guard<std::mutex> g(mmd::g_profile.mu);
+  mmd::g_profile.on = on != 0;
+  return MMD_OK;
+}
+
+extern "C" int mmd_profile_collect(float* ms_host, int cap) {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  {
+    std::lock_guard<std::mutex> g(mmd::g_profile.mu);
+    ev.swap(mmd::g_profile.events);
+  }
+  int n = 0;
+  for (auto& pr : ev) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess &&
+        ms_host != nullptr && n < cap) {
+      ms_host[n++] = ms;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  return n;
+}
+
+extern "C" size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op_dtype, int k) {
+  using namespace mmd;
+  (void)dim; (void)op_dtype;
+  if (Q <= 0 || N <= 0 || k <= 0 || cap_for_k(k) == 0) return 0;
+  // upper bound over every schedule the planner may choose: parts * k <= 4096 keys per query
+  const int64_t n_n = ceil_div(N, kTileN);
+  int64_t parts = 4096 / k;
+  if (parts > n_n) parts = n_n;
+  if (parts > 1024) parts = 1024;
+  if (parts < 1) parts = 1;
+  return static_cast<size_t>(Q) * parts * k * sizeof(uint64_t) + 256;
+}
+
+extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
+                               int k, int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k > 0, "mmd_topk_scores: Q=%lld N=%lld dim=%d k=%d", (long long)Q,
+              (long long)N, dim, k);
+  MMD_REQUIRE(N < (1ll << 31) && Q < (1ll << 31), "mmd_topk_scores: Q and N must be < 2^31");
+  MMD_REQUIRE(idx_offset >= 0 && idx_offset + N < (1ll << 31), "mmd_topk_scores: idx_offset + N must be < 2^31");
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(out_scores != nullptr && out_idx != nullptr, "mmd_topk_scores: null output");
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int cap = cap_for_k(k);
+  MMD_REQUIRE(cap != 0, "mmd_topk_scores: k=%d exceeds the fused selection limit %d", k, mmd_topk_max_k());
+  if (N == 0) {
+    // empty corpus: every slot is (-inf, -1)
+    return merge_partial_keys(nullptr, 0, Q, k, k, 1.0f, idx_offset, out_scores, out_idx, st);
+  }
+  MMD_REQUIRE(q_prep != nullptr && c_prep != nullptr, "mmd_topk_scores: null operand");
+  MMD_REQUIRE(reinterpret_cast<uintptr_t>(q_prep) % 16 == 0 && reinterpret_cast<uintptr_t>(c_prep) % 16 == 0,
+              "mmd_topk_scores: operands must be 16-byte aligned");
+  PreparedLayout lay;
+  MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_topk_scores: bad op_dtype %d", op_dtype);
+
+  const int sms = sm_count();
+  const Schedule sch = plan_schedule(Q, N, k, sms);
+  const size_t need = static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_last_error("mmd_topk_scores: workspace %zu < %zu bytes", workspace_bytes, need);
+    return MMD_ERR_WORKSPACE;
+  }
+  MMD_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 8 == 0, "mmd_topk_scores: workspace must be 8-byte aligned");
+
+  CUtensorMap tq, tc;
+  rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, kTileM);
+  if (rc != MMD_OK) return rc;
+  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN);
+  if (rc != MMD_OK) return rc;
+
+  FusedParams p{};
+  p.Q = Q; p.N = N;
+  p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
+  p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = sch.T; p.n_strips = sch.S; p.n_units = sch.n_units;
+  p.kprime = k;
+  p.stages = stages_for(cap);
+  p.partial = static_cast<uint64_t*>(workspace);
+  p.dense = nullptr; p.ldd = 0; p.out_scale = 1.0f;
+  p.status = device_status_word();
+  const uint32_t idesc = idesc_for(op_dtype);
+  const bool f8 = op_dtype == MMD_OP_E4M3;
+
+  if (cap == 32) rc = f8 ? launch_fused<32, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<32, false, false>(tq, tc, p, idesc, sch.grid, st);
+  else if (cap == 64) rc = f8 ? launch_fused<64, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<64, false, false>(tq, tc, p, idesc, sch.grid, st);
+  else rc = f8 ? launch_fused<128, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<128, false, false>(tq, tc, p, idesc, sch.grid, st);
+  if (rc != MMD_OK) return rc;
+
+  const float scale = f8 ? (1.0f / 65536.0f) : 1.0f;
+  return merge_partial_keys(p.partial, sch.S, Q, k, k, scale, idx_offset, out_scores, out_idx, st);
+}
+
+extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
+                                float* out_scores, int64_t ld_scores, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0, "mmd_scores_dense: Q=%lld N=%lld dim=%d", (long long)Q, (long long)N, dim);
+  MMD_REQUIRE(N < (1ll << 31) && Q < (1ll << 31), "mmd_scores_dense: Q and N must be < 2^31");
+  if (Q == 0 || N == 0) return MMD_OK;
+  MMD_REQUIRE(q_prep != nullptr && c_prep != nullptr && out_scores != nullptr, "mmd_scores_dense: null buffer");
+  MMD_REQUIRE(ld_scores >= N, "mmd_scores_dense: ld_scores %lld < N %lld", (long long)ld_scores, (long long)N);
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  PreparedLayout lay;
+  MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_scores_dense: bad op_dtype %d", op_dtype);
+  const int sms = sm_count();
+  Schedule sch{};
+  sch.n_m = static_cast<int>(ceil_div(Q, kTileM));
+  sch.n_n = static_cast<int>(ceil_div(N, kTileN));
+  sch.T = 1; sch.S = sch.n_n; sch.n_units = sch.n_m * sch.S;
+  sch.grid = sch.n_units < sms ? sch.n_units : sms;
+
+  CUtensorMap tq, tc;
+  rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, kTileM);
+  if (rc != MMD_OK) return rc;
+  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN);
+  if (rc != MMD_OK) return rc;
+
+  FusedParams p{};
+  p.Q = Q; p.N = N;
+  p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
+  p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = 1; p.n_strips = sch.S; p.n_units = sch.n_units;
+  p.kprime = 0;
+  p.stages = stages_for(0);
+  if (p.stages > 4) p.stages = 4;
+  p.partial = nullptr;
+  p.dense = out_scores; p.ldd = ld_scores;
+  const bool f8 = op_dtype == MMD_OP_E4M3;
+  p.out_scale = f8 ? (1.0f / 65536.0f) : 1.0f;
+  p.status = device_status_word();
+  const uint32_t idesc = idesc_for(op_dtype);
+  return f8 ? launch_fused<32, true, true>(tq, tc, p, idesc, sch.grid, st)
+            : launch_fused<32, false, true>(tq, tc, p, idesc, sch.grid, st);
+}

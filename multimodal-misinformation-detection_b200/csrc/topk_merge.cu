@@ -1,0 +1,184 @@
+// K3b / K4: fold partial top-K lists into one list per query.
+//
+// Two producers feed it: the strips of the fused kernel (keys, [Q][parts][k_in]) and the per-rank lists of
+// a row-sharded corpus after the all-gather ([parts][Q][k_in] decoded scores + rows).  The reference's
+// counterpart is the per-query heapq push / pushpop over 500k-row corpus chunks followed by sorted(...)
+// inside sentence_transformers.util.semantic_search (call sites src/evidence/text2text_retrieval.py:56-64),
+// and the list concat + sort of src/evidence/text2text_retrieval.py:97-110.
+//
+// One query per warp (<= 128 candidates, shuffle bitonic sort in registers) or per 256-thread block
+// (<= 4096 candidates, bitonic sort in shared memory).  Order: (score descending, row ascending).
+#include "common.cuh"
+
+namespace mmd {
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct MergeSrc {
+  const uint64_t* keys;   // [Q][parts * k_in]                    (keys != nullptr)
+  const float* scores;    // [parts][Q][k_in]                      (keys == nullptr)
+  const int32_t* idx;
+  int parts, k_in;
+  int64_t Q;
+};
+
+__device__ __forceinline__ uint64_t load_candidate(const MergeSrc& s, int64_t q, int i) {
+  if (i >= s.parts * s.k_in) return 0ull;
+  if (s.keys != nullptr) return s.keys[q * (static_cast<int64_t>(s.parts) * s.k_in) + i];
+  const int part = i / s.k_in, j = i - part * s.k_in;
+  const int64_t off = (static_cast<int64_t>(part) * s.Q + q) * s.k_in + j;
+  const int32_t r = s.idx[off];
+  return r < 0 ? 0ull : make_key(s.scores[off], static_cast<uint32_t>(r));
+}
+
+__device__ __forceinline__ void store_result(uint64_t key, float scale, int64_t idx_offset, float* out_s,
+                                             int32_t* out_i) {
+  if (key == 0ull) {
+    *out_s = __int_as_float(0xff800000);
+    *out_i = -1;
+  } else {
+    *out_s = key_score(key) * scale;
+    *out_i = static_cast<int32_t>(static_cast<int64_t>(key_row(key)) + idx_offset);
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[E], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int es = stride >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & es) == 0) {
+            const bool desc = ((e * 32 + lane) & size) == 0;
+            const uint64_t a = k[e], b = k[e | es];
+            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+            k[e] = desc ? mx : mn;
+            k[e | es] = desc ? mn : mx;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const uint64_t other = __shfl_xor_sync(kFull, k[e], stride);
+          const bool lower = (lane & stride) == 0;
+          const bool desc = ((e * 32 + lane) & size) == 0;
+          const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
+          k[e] = (lower == desc) ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(128)
+merge_warp_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, float* __restrict__ out_s,
+                  int32_t* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (q >= src.Q) return;
+  uint64_t k[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) k[e] = load_candidate(src, q, e * 32 + lane);
+  warp_bitonic_desc<E>(k, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < k_out) store_result(k[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+  }
+  // k_out beyond the candidate count: empty slots
+  for (int i = 32 * E + lane; i < k_out; i += 32) store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+merge_block_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, float* __restrict__ out_s,
+                   int32_t* __restrict__ out_i) {
+  __shared__ uint64_t keys[L];
+  const int64_t q = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += 256) keys[i] = load_candidate(src, q, i);
+  __syncthreads();
+  for (int size = 2; size <= L; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < L / 2; t += 256) {
+        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));   // lower index of the pair
+        const int j = i | stride;
+        const bool desc = (i & size) == 0;
+        const uint64_t a = keys[i], b = keys[j];
+        if ((a < b) == desc) { keys[i] = b; keys[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k_out; i += 256)
+    store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+}
+
+int launch_merge(const MergeSrc& src, int k_out, float scale, int64_t idx_offset, float* out_s, int32_t* out_i,
+                 cudaStream_t stream) {
+  const int total = src.parts * src.k_in;
+  const unsigned qblocks = static_cast<unsigned>(ceil_div(src.Q, 4));
+  if (total <= 32) merge_warp_kernel<1><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 64) merge_warp_kernel<2><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 128) merge_warp_kernel<4><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 256) merge_block_kernel<256><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 512) merge_block_kernel<512><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 1024) merge_block_kernel<1024><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 2048) merge_block_kernel<2048><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (total <= 4096) merge_block_kernel<4096><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else {
+    set_last_error("merge: %d candidates per query exceeds 4096", total);
+    return MMD_ERR_ARG;
+  }
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
+}
+
+}  // namespace
+
+int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
+                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream) {
+  MergeSrc src{};
+  src.keys = partial;
+  src.scores = nullptr;
+  src.idx = nullptr;
+  src.parts = partial == nullptr ? 0 : parts;
+  src.k_in = k_in;
+  src.Q = Q;
+  if (partial == nullptr) {
+    // no candidates at all: make load_candidate return "empty" for every slot
+    src.keys = reinterpret_cast<const uint64_t*>(out_scores);   // never dereferenced (parts == 0)
+  }
+  return launch_merge(src, k_out, scale, idx_offset, out_scores, out_idx, stream);
+}
+
+}  // namespace mmd
+
+extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts, int64_t Q, int k_in, int k_out,
+                              float* out_scores, int32_t* out_idx, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(parts > 0 && Q >= 0 && k_in > 0 && k_out > 0, "mmd_topk_merge: parts=%d Q=%lld k_in=%d k_out=%d", parts,
+              (long long)Q, k_in, k_out);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(scores != nullptr && idx != nullptr && out_scores != nullptr && out_idx != nullptr,
+              "mmd_topk_merge: null buffer");
+  MMD_REQUIRE(static_cast<int64_t>(parts) * k_in <= 4096, "mmd_topk_merge: parts*k_in = %lld exceeds 4096",
+              (long long)parts * k_in);
+  MMD_REQUIRE(k_out <= 4096, "mmd_topk_merge: k_out %d exceeds 4096", k_out);
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  MergeSrc src{};
+  src.keys = nullptr;
+  src.scores = scores;
+  src.idx = idx;
+  src.parts = parts;
+  src.k_in = k_in;
+  src.Q = Q;
+  return launch_merge(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,28 @@
+"""mmd_retrieval -- B200-native evidence retrieval (top-K cosine / inner product) for
+sakdag/multimodal-misinformation-detection's `src/evidence` path.
+
+Public surface (mirrors the reference's entry points; see DESIGN.md / INTEGRATION.md):
+
+    topk(queries, corpus, k, metric, dtype)        raw tensor contract  (scores, indices)
+    prepare_corpus(...) -> PreparedCorpus          normalise + cast once, keep resident in HBM
+    semantic_search(q, corpus, top_k=..)           drop-in for sentence_transformers.util.semantic_search
+    cos_sim / dot_score                            drop-in score functions
+    ImageCorpus / ImageSimilarity                  drop-in for src/evidence/im2im_retrieval.py
+    ShardedCorpus                                  row-sharded corpus over the GPUs of one box
+
+All arithmetic runs in libmmd.so (hand-written sm_100a CUDA behind a C ABI).  There is no CPU fallback.
+"""
+from ._lib import MmdError, LIB_PATH
+from .ops import (PreparedCorpus, prepare_corpus, topk, dense_scores, merge_topk, normalize_cast, max_k,
+                  profile_enable, profile_collect, launch_count)
+from .postfilter import dedupe_by_score, hits_at_k
+from .semantic_search import semantic_search, cos_sim, dot_score, clear_cache
+from .image_corpus import ImageCorpus, ImageSimilarity, calculate_topk_accuracy_image_retrieval
+from .sharded import ShardedCorpus, shard_bounds
+
+__all__ = [
+    "MmdError", "LIB_PATH", "PreparedCorpus", "prepare_corpus", "topk", "dense_scores", "merge_topk", "normalize_cast",
+    "max_k", "profile_enable", "profile_collect", "launch_count", "dedupe_by_score", "hits_at_k", "semantic_search",
+    "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "calculate_topk_accuracy_image_retrieval",
+    "ShardedCorpus", "shard_bounds",
+]

@@ -1,0 +1,265 @@
+"""Raw tensor API of the retrieval hot path (boundary B3 of SURVEY.md section 8b).
+
+    topk(queries[Q,D], corpus[N,D] | PreparedCorpus, k, metric, dtype, eps) -> (scores f32 [Q,k'], indices [Q,k'])
+
+with k' = min(k, N), scores sorted descending, ties by ascending corpus row.  It replaces, for a whole batch
+of queries at once, what the reference does one query at a time:
+
+  * sentence_transformers.util.semantic_search (normalise -> mm -> topk -> heap merge), called from
+    src/evidence/text2text_retrieval.py:56-64 and src/evidence/experiment_text.py:25-33;
+  * the per-pair nn.CosineSimilarity loop + full sort of src/evidence/im2im_retrieval.py:84-92 and
+    src/evidence/experiment_image.py:25-33.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libmmd.so (CUDA, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+
+_SRC_DTYPE = {torch.float32: _lib.SRC_F32, torch.float16: _lib.SRC_F16, torch.bfloat16: _lib.SRC_BF16}
+_OP_DTYPE = {"bf16": _lib.OP_BF16, "fp16": _lib.OP_F16, "fp8": _lib.OP_E4M3, "fp32": _lib.OP_BF16X3}
+METRICS = ("cos", "dot")
+
+#: default clamp of the norm: F.normalize's 1e-12 (text path); the image path passes nn.CosineSimilarity's 1e-6
+DEFAULT_EPS = 1e-12
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise _lib.MmdError(f"the retrieval path runs on a CUDA (sm_100) device only, got {device}; no CPU fallback")
+
+
+def _as_rows(x, device: Optional[torch.device] = None) -> torch.Tensor:
+    """list / ndarray / tensor -> 2-D tensor with unit inner stride on `device` (fp32/fp16/bf16)."""
+    if not isinstance(x, torch.Tensor):
+        import numpy as np
+        x = torch.as_tensor(np.asarray(x))
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    if x.dim() != 2:
+        raise ValueError(f"expected [rows, dim] embeddings, got shape {tuple(x.shape)}")
+    if x.dtype not in _SRC_DTYPE:
+        x = x.to(torch.float32)
+    if device is not None and x.device != device:
+        x = x.to(device, non_blocking=True)
+    if x.stride(1) != 1 and x.numel() > 0:
+        x = x.contiguous()
+    return x
+
+
+def prepared_layout(op: str, dim: int) -> Tuple[int, int]:
+    """(contraction length in operand elements, bytes per prepared row)."""
+    kdim, row_bytes = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.load().mmd_prepared_layout(_OP_DTYPE[op], dim, C.byref(kdim), C.byref(row_bytes)), "mmd_prepared_layout")
+    return kdim.value, row_bytes.value
+
+
+def normalize_cast(x: torch.Tensor, op: str, side: int, normalize: bool, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1: rows of `x` -> (prepared operand rows uint8 [rows, row_bytes], inv_norm f32 [rows])."""
+    _require_cuda(x.device)
+    rows, dim = x.shape
+    _, row_bytes = prepared_layout(op, dim)
+    out = torch.empty((rows, row_bytes), dtype=torch.uint8, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    if rows:
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            rc = lib.mmd_normalize_cast(_ptr(x), _SRC_DTYPE[x.dtype], rows, dim, x.stride(0), int(normalize), float(eps),
+                                        _OP_DTYPE[op], side, _ptr(out), _ptr(inv), _stream_ptr(x.device))
+        _lib.check(rc, "mmd_normalize_cast")
+    return out, inv
+
+
+@dataclass
+class PreparedCorpus:
+    """Corpus rows normalised and cast once, resident in HBM, ready for any number of query batches.
+
+    (The reference re-normalises the whole corpus inside every semantic_search call,
+    src/evidence/text2text_retrieval.py:56-63.)"""
+    rows: torch.Tensor            # uint8 [N, row_bytes] operand tiles
+    inv_norm: Optional[torch.Tensor]   # f32 [N] (None for metric="dot")
+    source: Optional[torch.Tensor]     # caller's embeddings on the device (for the exact re-score), or None
+    n: int
+    dim: int
+    op: str
+    metric: str
+    eps: float
+    idx_offset: int = 0           # global row of local row 0 (row-sharded corpora)
+
+    @property
+    def device(self) -> torch.device:
+        return self.rows.device
+
+
+def prepare_corpus(corpus, dtype: str = "bf16", metric: str = "cos", eps: float = DEFAULT_EPS, keep_source: bool = True,
+                   device: Optional[Union[str, torch.device]] = None, idx_offset: int = 0) -> PreparedCorpus:
+    if dtype not in _OP_DTYPE:
+        raise ValueError(f"dtype must be one of {sorted(_OP_DTYPE)}, got {dtype!r}")
+    if metric not in METRICS:
+        raise ValueError(f"metric must be one of {METRICS}, got {metric!r}")
+    if device is not None:
+        dev = torch.device(device)
+    elif isinstance(corpus, torch.Tensor) and corpus.is_cuda:
+        dev = corpus.device
+    elif torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        raise _lib.MmdError("no CUDA device is available; the retrieval path has no CPU fallback")
+    _require_cuda(dev)
+    c = _as_rows(corpus, dev)
+    rows, inv = normalize_cast(c, dtype, _lib.SIDE_CORPUS, metric == "cos", eps)
+    return PreparedCorpus(rows=rows, inv_norm=inv if metric == "cos" else None, source=c if keep_source else None,
+                          n=c.shape[0], dim=c.shape[1], op=dtype, metric=metric, eps=eps, idx_offset=idx_offset)
+
+
+def max_k() -> int:
+    return int(_lib.load().mmd_topk_max_k())
+
+
+def overfetch_for(k: int, n: int) -> int:
+    """Candidates kept by the low-precision pass when an exact re-score follows."""
+    return max(1, min(n, k + max(8, k // 2), max_k()))
+
+
+def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2+K3 (+K3b): fused contraction + top-k over prepared operands -> (scores f32 [Q,k], idx i32 [Q,k])."""
+    lib = _lib.load()
+    dev = corpus.device
+    scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_queries, k), dtype=torch.int32, device=dev)
+    if n_queries == 0:
+        return scores, idx
+    op = _OP_DTYPE[corpus.op]
+    ws_bytes = int(lib.mmd_topk_workspace_bytes(n_queries, max(corpus.n, 1), corpus.dim, op, k))
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mmd_topk_scores(_ptr(q_rows), _ptr(corpus.rows), op, n_queries, corpus.n, corpus.dim, k, corpus.idx_offset,
+                                 _ptr(scores), _ptr(idx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+    _lib.check(rc, "mmd_topk_scores")
+    return scores, idx
+
+
+def rescore(q: torch.Tensor, q_inv: Optional[torch.Tensor], corpus: PreparedCorpus, cand_idx: torch.Tensor,
+            k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K5: exact fp32 cosine / dot of the candidates from the original embeddings, re-ranked."""
+    lib = _lib.load()
+    dev = corpus.device
+    n_queries, k_in = cand_idx.shape
+    scores = torch.empty((n_queries, k_out), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_queries, k_out), dtype=torch.int32, device=dev)
+    if n_queries == 0:
+        return scores, idx
+    src = corpus.source
+    with torch.cuda.device(dev):
+        rc = lib.mmd_rescore(_ptr(q), _SRC_DTYPE[q.dtype], q.stride(0), _ptr(q_inv), _ptr(src), _SRC_DTYPE[src.dtype],
+                             src.stride(0) if src.shape[0] else corpus.dim, _ptr(corpus.inv_norm), n_queries, corpus.n, corpus.dim,
+                             _ptr(cand_idx), k_in, corpus.idx_offset, k_out, _ptr(scores), _ptr(idx), _stream_ptr(dev))
+    _lib.check(rc, "mmd_rescore")
+    return scores, idx
+
+
+def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None,
+         rescore_exact: Optional[bool] = None, overfetch: Optional[int] = None,
+         index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k most similar corpus rows for every query.
+
+    queries : [Q,D] (or [D]) tensor / ndarray / list, any device (moved to the corpus device).
+    corpus  : [N,D] embeddings (prepared on the fly) or a PreparedCorpus (prepared once, reused).
+    returns : scores f32 [Q, min(k,N)] descending, indices [Q, min(k,N)] (rows of `corpus`, + idx_offset).
+
+    rescore_exact (default: on when the corpus kept its source embeddings) over-fetches candidates with the
+    tensor-core pass and recomputes their scores in fp32 from the original embeddings.
+    """
+    if k <= 0:
+        raise ValueError("k must be positive")
+    if isinstance(corpus, PreparedCorpus):
+        pc = corpus
+    else:
+        pc = prepare_corpus(corpus, dtype=dtype, metric=metric, eps=DEFAULT_EPS if eps is None else eps)
+    q = _as_rows(queries, pc.device)
+    if q.shape[1] != pc.dim:
+        raise RuntimeError(f"query dim {q.shape[1]} does not match corpus dim {pc.dim}")
+    n_queries = q.shape[0]
+    k_eff = min(k, pc.n)
+    if k_eff == 0:
+        return (torch.empty((n_queries, 0), dtype=torch.float32, device=pc.device),
+                torch.empty((n_queries, 0), dtype=index_dtype, device=pc.device))
+    if k_eff > max_k():
+        raise _lib.MmdError(f"k={k_eff} exceeds the fused top-k limit {max_k()} (use dense_scores for a full ranking)")
+    do_rescore = (pc.source is not None) if rescore_exact is None else bool(rescore_exact)
+    if do_rescore and pc.source is None:
+        raise ValueError("rescore_exact=True needs a PreparedCorpus built with keep_source=True")
+    kprime = k_eff
+    if do_rescore:
+        kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
+    q_rows, q_inv = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
+    scores, idx = topk_prepared(q_rows, n_queries, pc, kprime)
+    if do_rescore:
+        scores, idx = rescore(q, q_inv if pc.metric == "cos" else None, pc, idx, k_eff)
+    elif kprime != k_eff:
+        scores, idx = scores[:, :k_eff].contiguous(), idx[:, :k_eff].contiguous()
+    if index_dtype != torch.int32:
+        idx = idx.to(index_dtype)
+    return scores, idx
+
+
+def dense_scores(queries, corpus, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None) -> torch.Tensor:
+    """Full [Q,N] fp32 score matrix from the same tensor-core contraction (small shapes only)."""
+    pc = corpus if isinstance(corpus, PreparedCorpus) else prepare_corpus(
+        corpus, dtype=dtype, metric=metric, eps=DEFAULT_EPS if eps is None else eps, keep_source=False)
+    q = _as_rows(queries, pc.device)
+    if q.shape[1] != pc.dim:
+        raise RuntimeError(f"query dim {q.shape[1]} does not match corpus dim {pc.dim}")
+    out = torch.empty((q.shape[0], pc.n), dtype=torch.float32, device=pc.device)
+    if out.numel() == 0:
+        return out
+    q_rows, _ = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
+    with torch.cuda.device(pc.device):
+        rc = _lib.load().mmd_scores_dense(_ptr(q_rows), _ptr(pc.rows), _OP_DTYPE[pc.op], q.shape[0], pc.n, pc.dim, _ptr(out),
+                                          out.stride(0), _stream_ptr(pc.device))
+    _lib.check(rc, "mmd_scores_dense")
+    return out
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4: merge [parts, Q, k_in] partial lists (e.g. all-gathered per-rank results) -> [Q, k_out]."""
+    _require_cuda(scores.device)
+    parts, n_queries, k_in = scores.shape
+    scores = scores.contiguous().float()
+    idx = idx.contiguous().to(torch.int32)
+    out_s = torch.empty((n_queries, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=scores.device)
+    if n_queries:
+        with torch.cuda.device(scores.device):
+            rc = _lib.load().mmd_topk_merge(_ptr(scores), _ptr(idx), parts, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
+                                            _stream_ptr(scores.device))
+        _lib.check(rc, "mmd_topk_merge")
+    return out_s, out_i
+
+
+def profile_enable(on: bool) -> None:
+    _lib.load().mmd_profile_enable(int(on))
+
+
+def profile_collect(cap: int = 512):
+    buf = (C.c_float * cap)()
+    n = _lib.load().mmd_profile_collect(buf, cap)
+    return [float(buf[i]) for i in range(n)]
+
+
+def launch_count() -> int:
+    return int(_lib.load().mmd_launch_count())
