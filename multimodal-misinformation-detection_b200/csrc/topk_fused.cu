@@ -410,9 +410,10 @@ struct Schedule {
   int n_m, n_n, T, S, n_units, grid;
 };
 
-// Pick the strip length: static round-robin of units over `sms` CTAs; minimise the busiest CTA's tile
-// count, then prefer fewer strips (fewer list restarts and a cheaper merge).
-Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms) {
+// Pick the strip length.  Units are dealt round-robin to `sms` persistent CTAs; the cost of a schedule is
+// the busiest CTA's tile count plus a per-unit restart charge (list warm-up + final sort + the extra
+// strip the merge has to fold), expressed in tiles.  Fewer strips win ties.
+Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks) {
   Schedule s{};
   s.n_m = static_cast<int>(ceil_div(Q, kTileM));
   s.n_n = static_cast<int>(ceil_div(N, kTileN));
@@ -420,12 +421,11 @@ Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms) {
   int s_max = s.n_n < max_parts ? s.n_n : max_parts;
   if (s_max > 1024) s_max = 1024;
   if (s_max < 1) s_max = 1;
-  int64_t best_load = -1;
+  // restart charge: ~8k cycles against kblocks * 512 cycles of MMA per tile, at least a quarter tile
+  double restart = 8000.0 / (static_cast<double>(kblocks > 0 ? kblocks : 1) * 512.0);
+  if (restart < 0.25) restart = 0.25;
+  double best_cost = -1.0;
   int best_S = 1, best_T = s.n_n;
-  // first pass: find the minimal busiest-CTA load
-  struct Cand { int S, T; int64_t load; };
-  Cand cands[1024];
-  int nc = 0;
   int last_T = -1;
   for (int S = 1; S <= s_max; ++S) {
     const int T = static_cast<int>(ceil_div(s.n_n, S));
@@ -435,24 +435,19 @@ Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms) {
     const int64_t units = static_cast<int64_t>(s.n_m) * S_eff;
     const int G = static_cast<int>(units < sms ? units : sms);
     const int T_last = s.n_n - (S_eff - 1) * T;
-    int64_t worst = 0;
+    const int64_t lo = units - s.n_m;   // first unit of the last (possibly shorter) strip
+    double worst = 0.0;
     for (int c = 0; c < G; ++c) {
       const int64_t cnt = (units - 1 - c) / G + 1;
-      // units of CTA c that lie in the last strip: u in [units - n_m, units), u % G == c
-      const int64_t lo = units - s.n_m;
-      int64_t first = lo + ((c - lo % G) % G + G) % G;
+      const int64_t first = lo + ((c - lo % G) % G + G) % G;
       const int64_t in_last = first < units ? (units - 1 - first) / G + 1 : 0;
-      const int64_t load = (cnt - in_last) * T + in_last * T_last;
-      if (load > worst) worst = load;
+      const double cost = static_cast<double>((cnt - in_last) * T + in_last * T_last) + restart * static_cast<double>(cnt);
+      if (cost > worst) worst = cost;
     }
-    cands[nc++] = {S_eff, T, worst};
-    if (best_load < 0 || worst < best_load) best_load = worst;
-  }
-  for (int i = 0; i < nc; ++i) {
-    if (cands[i].load * 100 <= best_load * 102) {   // within 2% of the best balance: take the fewest strips
-      best_S = cands[i].S;
-      best_T = cands[i].T;
-      break;
+    if (best_cost < 0.0 || worst < best_cost * 0.999) {
+      best_cost = worst;
+      best_S = S_eff;
+      best_T = T;
     }
   }
   s.S = best_S;
@@ -532,8 +527,10 @@ int stages_for(int cap) {
 
 int sm_count() {
   int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();   // no device (CPU-only host): plan for a B200's 148 SMs
+    sms = 148;
+  }
   return sms;
 }
 
@@ -575,15 +572,12 @@ extern "C" int mmd_profile_collect(float* ms_host, int cap) {
 
 extern "C" size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op_dtype, int k) {
   using namespace mmd;
-  (void)dim; (void)op_dtype;
   if (Q <= 0 || N <= 0 || k <= 0 || cap_for_k(k) == 0) return 0;
-  // upper bound over every schedule the planner may choose: parts * k <= 4096 keys per query
-  const int64_t n_n = ceil_div(N, kTileN);
-  int64_t parts = 4096 / k;
-  if (parts > n_n) parts = n_n;
-  if (parts > 1024) parts = 1024;
-  if (parts < 1) parts = 1;
-  return static_cast<size_t>(Q) * parts * k * sizeof(uint64_t) + 256;
+  // exactly what mmd_topk_scores will carve up: one K-list per (query, strip) of the planned schedule
+  PreparedLayout lay;
+  if (!prepared_layout(op_dtype, dim, &lay)) return 0;
+  const Schedule sch = plan_schedule(Q, N, k, sm_count(), static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)));
+  return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + 256;
 }
 
 extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
@@ -612,7 +606,7 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_topk_scores: bad op_dtype %d", op_dtype);
 
   const int sms = sm_count();
-  const Schedule sch = plan_schedule(Q, N, k, sms);
+  const Schedule sch = plan_schedule(Q, N, k, sms, static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)));
   const size_t need = static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t);
   if (workspace == nullptr || workspace_bytes < need) {
     set_last_error("mmd_topk_scores: workspace %zu < %zu bytes", workspace_bytes, need);
