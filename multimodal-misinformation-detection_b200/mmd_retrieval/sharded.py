@@ -81,8 +81,9 @@ class ShardedCorpus:
             return s_loc, i_loc.to(torch.int64)
         # one collective: (score bits, row) packed as int32 pairs -> Q * k * 8 bytes per rank
         packed = torch.stack([s_loc.view(torch.int32), i_loc], dim=-1).contiguous()
-        gathered = torch.empty((self.world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        gathered = torch.empty((self.world * n_queries,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)      # rank-major concatenation along dim 0
+        gathered = gathered.view((self.world, n_queries) + tuple(packed.shape[1:]))
         s_all = gathered[..., 0].contiguous().view(torch.float32)
         i_all = gathered[..., 1].contiguous()
         s, i = self._merge(s_all, i_all, k_glob)

@@ -37,7 +37,8 @@ def make_im2im(name: str, seed: int, n_corpus: int, n_query: int, dim: int, top_
     for z in range(n_zero):          # degenerate all-zero feature rows (norm clamp path)
         corpus[n_corpus // 2 + z] = 0.0
     queries = _image_like(gen, n_query, dim)
-    queries[0] = corpus[3] * 1.5     # an exact (scaled) match: cosine 1
+    queries[0] = corpus[3] * 2.0     # an exact (scaled) match: cosine 1
+    corpus, queries = corpus.half().float(), queries.half().float()   # what the npz stores, losslessly
     feature_dict = {f"c{idx:05d}": corpus[idx].clone() for idx in range(n_corpus)}
     qdict = {f"q{idx:03d}": queries[idx].clone() for idx in range(n_query)}
     res = im2im.reference_retrieve(feature_dict, qdict, top_k)

@@ -1,0 +1,364 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes -> libmmd.so), against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  * index sets identical to the oracle except at score near-ties (oracle.exact.compare_topk);
+  * scores within 1e-5 relative for the fp32 configuration and for every result that went through the exact
+    re-score (the default); raw bf16 tensor-core scores within 1e-3 relative on image-like (non-negative) features,
+    and within 1e-3 of the unit-norm scale on near-orthogonal Gaussian pairs (operand rounding is relative to
+    ||q||*||c|| = 1, not to a score that is itself ~0.1 -- see DESIGN.md "Numerics").
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import evalmetrics, exact, im2im, st_util
+
+pytestmark = pytest.mark.gpu
+
+FP32_RTOL = 1e-5
+BF16_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mmd_retrieval
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert mmd_retrieval.LIB_PATH.exists(), "libmmd.so must be built in-tree"
+    return mmd_retrieval
+
+
+def _data(kind, rows, dim, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, dim, generator=gen)
+    return torch.relu(x) if kind == "image" else x
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("dim", [768, 2048, 100, 8, 4100])
+@pytest.mark.parametrize("src", [torch.float32, torch.float16, torch.bfloat16])
+def test_normalize_cast_bf16(m, dim, src):
+    from mmd_retrieval import _lib
+    x = _data("text", 333, dim, dim).to(src)
+    x[5] = 0                                           # zero row -> clamp path, output 0
+    x[6] = 1e-20 if src == torch.float32 else x[6]     # norm below eps
+    rows, inv = m.normalize_cast(x.cuda(), "bf16", _lib.SIDE_CORPUS, True, 1e-12)
+    got = rows.view(torch.bfloat16).float().cpu()
+    want32 = torch.nn.functional.normalize(x.float(), p=2, dim=1, eps=1e-12)
+    want = want32.to(torch.bfloat16).float()
+    assert got.shape[1] >= dim and torch.count_nonzero(got[:, dim:]) == 0          # K padding is zero
+    d = (got[:, :dim] - want).abs()
+    # identical up to the last-place rounding of the norm: at most one bf16 ulp, on a vanishing fraction
+    assert float((d > 0).float().mean()) < 2e-3
+    assert bool((d <= want.abs() * 2 ** -7 + 1e-30).all())
+    assert torch.count_nonzero(got[5]) == 0
+    want_inv = 1.0 / x.float().norm(dim=1).clamp_min(1e-12)
+    torch.testing.assert_close(inv.cpu(), want_inv, rtol=1e-6, atol=0)
+
+
+def test_normalize_cast_layouts(m):
+    from mmd_retrieval import _lib
+    x = _data("text", 64, 200, 1)
+    xn = torch.nn.functional.normalize(x, p=2, dim=1, eps=1e-12)
+    # fp16 operands
+    r16, _ = m.normalize_cast(x.cuda(), "fp16", _lib.SIDE_QUERY, True, 1e-12)
+    assert float((r16.view(torch.float16).float().cpu()[:, :200] - xn.half().float()).abs().max()) <= 2 ** -11
+    # fp8 operands carry a fixed 2^8 scale
+    r8, _ = m.normalize_cast(x.cuda(), "fp8", _lib.SIDE_CORPUS, True, 1e-12)
+    got8 = r8.view(torch.float8_e4m3fn).float().cpu()[:, :200] / 256
+    want8 = (xn * 256).to(torch.float8_e4m3fn).float() / 256
+    assert float((got8 != want8).float().mean()) < 2e-3
+    # fp32 configuration: three bf16 limbs reconstruct the fp32 value; limb order differs per side
+    kd, rb = m.ops.prepared_layout("fp32", 200)
+    dpad = kd // 6
+    for side, order in ((_lib.SIDE_QUERY, (2, 0, 1, 1, 0, 0)), (_lib.SIDE_CORPUS, (0, 2, 1, 0, 1, 0))):
+        r, _ = m.normalize_cast(x.cuda(), "fp32", side, True, 1e-12)
+        seg = r.view(torch.bfloat16).float().cpu().view(64, 6, dpad)[:, :, :200]
+        limb = {order[s]: seg[:, s] for s in range(6)}
+        rec = limb[0] + limb[1] + limb[2]
+        assert float((rec - xn).abs().max()) <= 2 ** -24
+        for s in range(6):
+            assert torch.equal(seg[:, s], limb[order[s]])
+    # metric="dot": no normalisation; strided source rows
+    big = _data("text", 32, 512, 2).cuda()
+    view = big[:, :256]
+    rd, inv = m.normalize_cast(view, "bf16", _lib.SIDE_CORPUS, False, 1e-12)
+    assert torch.equal(rd.view(torch.bfloat16).float().cpu(), view.cpu().to(torch.bfloat16).float())
+    assert torch.equal(inv.cpu(), torch.ones(32))
+
+
+# ------------------------------------------------------------------------------------------ K2 (dense)
+@pytest.mark.parametrize("op,tol", [("bf16", 2e-6), ("fp16", 2e-6), ("fp8", 2e-6), ("fp32", 2e-6)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 1000, 200), (129, 257, 768), (37, 41, 2048)])
+def test_dense_scores_match_operand_rounded_oracle(m, op, tol, shape):
+    q_n, c_n, dim = shape
+    q, c = _data("text", q_n, dim, 1), _data("text", c_n, dim, 2)
+    got = m.dense_scores(q.cuda(), c.cuda(), metric="cos", dtype=op).cpu().double()
+    want = exact.exact_scores(q, c, "cos", 1e-12, operand=None if op == "fp32" else op)
+    # same operands, fp32 tensor-core accumulation vs float64: only accumulation rounding remains.
+    # (K1's last-place norm rounding can move one operand by an ulp on rare elements -> allow that through atol.)
+    atol = {"bf16": 6e-5, "fp16": 8e-6, "fp8": 8e-4, "fp32": tol}[op]
+    assert float((got - want).abs().max()) <= atol
+    if op == "fp32":
+        rel = ((got - want).abs() / want.abs().clamp_min(1e-3)).max()
+        assert float(rel) <= FP32_RTOL
+
+
+def test_dense_dot_metric_and_pairwise_similarity(m):
+    q, c = _data("text", 10, 96, 3), _data("text", 20, 96, 4)
+    got = m.dense_scores(q.cuda(), c.cuda(), metric="dot", dtype="fp32").cpu().double()
+    want = q.double() @ c.double().T
+    assert float(((got - want).abs() / want.abs().clamp_min(1.0)).max()) <= FP32_RTOL
+    g = load_golden("im2im_a.npz")
+    sim = m.ImageSimilarity()
+    for i, want_s in enumerate(g["pair_scores"]):
+        assert sim.similarity(g["queries_t"][i], g["corpus_t"][i]) == pytest.approx(want_s, rel=FP32_RTOL)
+    dim = g["corpus_t"].shape[1]
+    assert sim.similarity(torch.zeros(dim), torch.ones(dim)) == 0.0
+    tiny = torch.full((dim,), 1e-8)
+    assert sim.similarity(tiny, tiny) == pytest.approx(g["edge_scores"][0], rel=1e-3)   # per-norm clamp, eps=1e-6
+
+
+# ------------------------------------------------------------------------------------------ K2+K3 fused top-K
+CASES = [
+    # kind,  Q,    N,     D,   k,  op
+    ("text", 1000, 10000, 768, 5, "fp32"),      # config 1 shape
+    ("text", 300, 5000, 768, 10, "bf16"),
+    ("image", 256, 6000, 2048, 10, "bf16"),     # config 2 shape, scaled down
+    ("text", 64, 20000, 768, 100, "bf16"),      # eval over-fetch (experiment_text.py:26)
+    ("text", 40, 3000, 512, 25, "fp16"),
+    ("text", 129, 257, 64, 7, "bf16"),          # one past every tile edge
+    ("text", 127, 255, 100, 7, "bf16"),         # D not a multiple of 8
+    ("text", 1, 41256, 768, 50, "bf16"),        # one query, the reference's usage pattern
+]
+
+
+@pytest.mark.parametrize("kind,q_n,c_n,dim,k,op", CASES)
+def test_topk_raw_matches_operand_rounded_oracle(m, kind, q_n, c_n, dim, k, op):
+    """No re-score: the fused kernel's own selection vs the oracle fed the same rounded operands."""
+    q, c = _data(kind, q_n, dim, 10), _data(kind, c_n, dim, 11)
+    eps = 1e-6 if kind == "image" else 1e-12
+    pc = m.prepare_corpus(c.cuda(), dtype=op, eps=eps, keep_source=False)
+    s, i = m.topk(q.cuda(), pc, k, rescore_exact=False)
+    assert s.dtype == torch.float32 and i.dtype == torch.int64 and tuple(s.shape) == (q_n, min(k, c_n))
+    full = exact.exact_scores(q, c, "cos", eps, operand=None if op == "fp32" else op)
+    cmp = exact.compare_topk(s, i, full, k, tie_tol=3e-6)
+    assert cmp.ok, cmp
+    assert cmp.identical_sets + cmp.excused_rows == q_n
+    assert cmp.max_score_err <= 6e-5, cmp
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+
+
+@pytest.mark.parametrize("kind,q_n,c_n,dim,k,op", CASES)
+def test_topk_default_path_matches_fp32_reference(m, kind, q_n, c_n, dim, k, op):
+    """Default path (tensor-core selection + exact re-score) vs the float64 ground truth AND the restated
+    reference semantic_search (fp32): identical index sets up to near-ties, scores within 1e-5 relative."""
+    q, c = _data(kind, q_n, dim, 10), _data(kind, c_n, dim, 11)
+    eps = 1e-6 if kind == "image" else 1e-12
+    s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype=op, eps=eps), k)
+    full = exact.exact_scores(q, c, "cos", eps)
+    cmp = exact.compare_topk(s, i, full, k, tie_tol=2e-6)
+    assert cmp.ok, cmp
+    assert cmp.max_rel_score_err <= FP32_RTOL, cmp
+    if kind == "text" and q_n <= 300:
+        hits = st_util.semantic_search(q, c, top_k=k)
+        ref_idx = torch.tensor([[h["corpus_id"] for h in hl] for hl in hits])
+        ref_s = torch.tensor([[h["score"] for h in hl] for hl in hits])
+        cmp2 = exact.compare_topk(ref_s, ref_idx, full, k, tie_tol=2e-6)
+        assert cmp2.ok
+        agree = sum(set(a) == set(b) for a, b in zip(ref_idx.tolist(), i.cpu().tolist()))
+        assert agree >= q_n - cmp.excused_rows - cmp2.excused_rows
+
+
+def test_raw_bf16_scores_within_1e3_relative_on_image_features(m):
+    q, c = _data("image", 128, 2048, 20), _data("image", 4000, 2048, 21)
+    s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype="bf16", eps=1e-6, keep_source=False), 10, rescore_exact=False)
+    full = exact.exact_scores(q, c, "cos", 1e-6)
+    picked = torch.gather(full, 1, i.cpu())
+    assert float(((s.cpu().double() - picked).abs() / picked.abs()).max()) <= BF16_RTOL
+    # Gaussian (near-orthogonal) pairs: error is relative to ||q||*||c|| = 1
+    q, c = _data("text", 128, 768, 22), _data("text", 4000, 768, 23)
+    s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype="bf16", keep_source=False), 10, rescore_exact=False)
+    picked = torch.gather(exact.exact_scores(q, c), 1, i.cpu())
+    assert float((s.cpu().double() - picked).abs().max()) <= BF16_RTOL
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_edge_cases(m):
+    # K > N, N = 1, Q = 1, K = 1
+    c = _data("text", 7, 64, 30)
+    q = _data("text", 5, 64, 31)
+    s, i = m.topk(q.cuda(), c.cuda(), 10)
+    assert tuple(s.shape) == (5, 7)
+    assert torch.equal(i.cpu(), exact.exact_topk(q, c, 10)[1])
+    s, i = m.topk(q[:1].cuda(), c[:1].cuda(), 3)
+    assert tuple(i.shape) == (1, 1) and int(i) == 0
+    s, i = m.topk(q[0].cuda(), c.cuda(), 1)                       # 1-D query is unsqueezed
+    assert tuple(i.shape) == (1, 1) and int(i) == int(exact.exact_topk(q[:1], c, 1)[1])
+    # empty query batch / empty corpus
+    s, i = m.topk(torch.empty(0, 64).cuda(), c.cuda(), 3)
+    assert tuple(s.shape) == (0, 3)
+    s, i = m.topk(q.cuda(), torch.empty(0, 64).cuda(), 3)
+    assert tuple(s.shape) == (5, 0)
+    # zero query row: every score is 0 -> ties -> ascending rows
+    z = torch.zeros(1, 64)
+    s, i = m.topk(z.cuda(), c.cuda(), 4)
+    assert i.cpu().tolist() == [[0, 1, 2, 3]] and torch.count_nonzero(s) == 0
+    # duplicate corpus rows: equal scores come back in ascending row order (the reference's stable sort)
+    c2 = _data("text", 600, 64, 32)
+    c2[500] = c2[3]
+    c2[100] = c2[3]
+    for rescore in (False, True):
+        s, i = m.topk(c2[3:4].cuda() * 3.0, m.prepare_corpus(c2.cuda(), dtype="bf16"), 5, rescore_exact=rescore)
+        assert i.cpu().tolist()[0][:3] == [3, 100, 500]
+        assert float(s[0, 0]) == float(s[0, 1]) == float(s[0, 2])
+    # all rows identical: pure tie-breaking across tiles and strips
+    same = torch.ones(3000, 64)
+    s, i = m.topk(torch.ones(2, 64).cuda(), same.cuda(), 20, rescore_exact=False)
+    assert i.cpu().tolist() == [list(range(20))] * 2
+    # the largest supported K, and one beyond
+    big = _data("text", 2000, 64, 33)
+    s, i = m.topk(q.cuda(), m.prepare_corpus(big.cuda(), keep_source=False), 120)
+    assert torch.equal(i.cpu(), exact.exact_topk(q, big, 120, operand="bf16")[1]) or \
+        exact.compare_topk(s, i, exact.exact_scores(q, big, operand="bf16"), 120, 3e-6).ok
+    with pytest.raises(m.MmdError):
+        m.topk(q.cuda(), big.cuda(), 121)
+    with pytest.raises(RuntimeError):
+        m.topk(torch.ones(2, 32).cuda(), big.cuda(), 3)           # dim mismatch, like torch.mm upstream
+    # inner-product metric
+    s, i = m.topk(q.cuda(), m.prepare_corpus(big.cuda(), dtype="fp32", metric="dot"), 6)
+    want_s, want_i = exact.exact_topk(q, big, 6, metric="dot")
+    assert torch.equal(i.cpu(), want_i)
+    assert float(((s.cpu().double() - want_s).abs() / want_s.abs()).max()) <= FP32_RTOL
+
+
+# ------------------------------------------------------------------------------------------ K3b / K4 / K5
+def test_merge_kernel(m):
+    gen = torch.Generator().manual_seed(40)
+    for parts, n_q, k_in, k_out in [(2, 50, 10, 10), (8, 33, 100, 100), (3, 7, 5, 12), (37, 9, 18, 18), (1, 4, 4, 2)]:
+        s = torch.randn(parts, n_q, k_in, generator=gen).round(decimals=1)       # plenty of equal scores
+        idx = torch.stack([torch.stack([torch.randperm(1000, generator=gen)[:k_in] for _ in range(n_q)]) + 1000 * p
+                           for p in range(parts)]).to(torch.int32)
+        idx[0, 0, -2:] = -1
+        s[0, 0, -2:] = float("-inf")
+        got_s, got_i = m.merge_topk(s.cuda(), idx.cuda(), k_out)
+        flat_s = s.permute(1, 0, 2).reshape(n_q, -1)
+        flat_i = idx.permute(1, 0, 2).reshape(n_q, -1).long()
+        for r in range(n_q):
+            cand = sorted(((-float(a), int(b)) for a, b in zip(flat_s[r], flat_i[r]) if b >= 0))[:k_out]
+            want_i = [b for _, b in cand] + [-1] * (k_out - len(cand))
+            want_s = [-a for a, _ in cand] + [float("-inf")] * (k_out - len(cand))
+            assert got_i[r].cpu().tolist() == want_i
+            assert got_s[r].cpu().tolist() == want_s
+
+
+def test_sharded_equals_unsharded(m):
+    """Row-sharding invariance on one GPU: per-shard top-K with global offsets + K4 merge == unsharded top-K."""
+    q, c = _data("text", 200, 768, 50), _data("text", 9001, 768, 51)
+    want_s, want_i = m.topk(q.cuda(), c.cuda(), 10)
+    from mmd_retrieval.sharded import shard_bounds
+    ss, ii = [], []
+    for r in range(3):
+        lo, hi = shard_bounds(c.shape[0], 3, r)
+        pc = m.prepare_corpus(c[lo:hi].cuda(), idx_offset=lo)
+        s, i = m.topk(q.cuda(), pc, 10, index_dtype=torch.int32)
+        assert int(i.min()) >= lo and int(i.max()) < hi
+        ss.append(s)
+        ii.append(i)
+    s, i = m.merge_topk(torch.stack(ss), torch.stack(ii), 10)
+    assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
+
+
+# ------------------------------------------------------------------------------------------ drop-in surfaces
+@pytest.mark.parametrize("name", ["im2im_a.npz", "im2im_b.npz"])
+def test_image_corpus_matches_reference_golden(m, name):
+    """ImageCorpus.retrieve_similar_images == the reference's own output (golden made by its code)."""
+    g = load_golden(name)
+    fd = {f"c{i:05d}": g["corpus_t"][i] for i in range(g["corpus_t"].shape[0])}
+    top_k = int(g["top_k"])
+
+    class Extractor:
+        def extract_features(self, path):
+            return g["queries_t"][int(path[1:])]
+
+    for dtype in ("bf16", "fp32"):
+        corpus = m.ImageCorpus(feature_dict=fd, feature_extractor=Extractor(), dtype=dtype)
+        for qi in range(g["queries_t"].shape[0]):
+            got = corpus.retrieve_similar_images(f"q{qi:03d}", top_k=top_k)
+            want_rows = [r for r in g["rows"][qi].tolist() if r >= 0]
+            assert [int(k[1:]) for k, _ in got] == want_rows, (dtype, qi)
+            np.testing.assert_allclose([s for _, s in got], g["scores"][qi][: len(got)], rtol=FP32_RTOL, atol=0)
+    batched = corpus.retrieve_similar_features(g["queries_t"], top_k)
+    assert [[int(k[1:]) for k, _ in lst] for lst in batched] == [[r for r in row.tolist() if r >= 0] for row in g["rows"]]
+
+
+def test_semantic_search_drop_in(m):
+    g = load_golden("t2t_fp32.npz")
+    q, c = torch.from_numpy(g["queries"]).float(), torch.from_numpy(g["corpus"]).float()
+    hits = m.semantic_search(q, c, top_k=int(g["top_k"]), dtype="fp32")
+    assert len(hits) == q.shape[0] and all(len(h) == int(g["top_k"]) for h in hits)
+    assert isinstance(hits[0][0]["corpus_id"], int) and isinstance(hits[0][0]["score"], float)
+    np.testing.assert_array_equal([[h["corpus_id"] for h in hl] for hl in hits], g["rows"])
+    np.testing.assert_allclose([[h["score"] for h in hl] for hl in hits], g["scores"], rtol=FP32_RTOL)
+    # default bf16 selection + re-score gives the same lists
+    hits_bf16 = m.semantic_search(q, c, top_k=int(g["top_k"]))
+    np.testing.assert_array_equal([[h["corpus_id"] for h in hl] for hl in hits_bf16], g["rows"])
+    # the reference's calling pattern: one fp16 1-D query per call, fp16 CPU corpus, repeated calls (cache)
+    g16 = load_golden("t2t_fp16.npz")
+    q16, c16 = torch.from_numpy(g16["queries"]), torch.from_numpy(g16["corpus"])
+    full = exact.exact_scores(q16.float(), c16.float())
+    k = int(g16["top_k"])
+    launches0 = m.launch_count()
+    for qi in range(4):
+        h = m.semantic_search(q16[qi], c16, top_k=k)[0]
+        cmp = exact.compare_topk(torch.tensor([[x["score"] for x in h]]), torch.tensor([[x["corpus_id"] for x in h]]),
+                                 full[qi:qi + 1], k, tie_tol=2e-6)
+        assert cmp.ok and cmp.max_rel_score_err <= FP32_RTOL
+        # and against the reference-dtype (fp16) golden: same sets up to fp16 near-ties
+        ref = exact.compare_topk(torch.from_numpy(g16["scores"][qi:qi + 1]), torch.from_numpy(g16["rows"][qi:qi + 1]),
+                                 full[qi:qi + 1], k, tie_tol=2e-3)
+        assert ref.ok
+    # corpus prepared once (1 K1 launch), then per call: K1(query) + fused + merge + rescore
+    assert m.launch_count() - launches0 == 1 + 4 * 4
+    # top_k > N and dot_score
+    few = m.semantic_search(q[:2], c[:3], top_k=10)
+    assert [len(h) for h in few] == [3, 3]
+    d = m.semantic_search(q[:3], c, top_k=4, score_function=m.dot_score, dtype="fp32")
+    want = st_util.semantic_search(q[:3], c, top_k=4, score_function=st_util.dot_score)
+    assert [[h["corpus_id"] for h in hl] for hl in d] == [[h["corpus_id"] for h in hl] for hl in want]
+    cs = m.cos_sim(q[:5], c[:9]).cpu()
+    torch.testing.assert_close(cs, st_util.cos_sim(q[:5], c[:9]), rtol=FP32_RTOL, atol=1e-6)
+
+
+def test_factify_shaped_topk_accuracy_matches_oracle(m):
+    """hits@{1,2,5,10} with the gold-exempt dedupe (experiment_image.py:41-61) on planted-positive synthetic data:
+    the GPU path and the CPU oracle must produce the same accuracy dict."""
+    gen = torch.Generator().manual_seed(60)
+    n, n_q, dim = 5000, 300, 2048
+    c = torch.relu(torch.randn(n, dim, generator=gen))
+    gold_rows = torch.randperm(n, generator=gen)[:n_q]
+    sigma = torch.linspace(0.3, 3.0, n_q)[:, None]                 # from easy to hopeless queries
+    q = torch.relu(c[gold_rows] + sigma * torch.randn(n_q, dim, generator=gen))
+    for j in range(40):                                            # duplicated evidences (identical scores)
+        c[(int(gold_rows[j]) + 1) % n] = c[int(gold_rows[j])]
+    keys = [f"img{i}" for i in range(n)]
+    gold_keys = [keys[int(r)] for r in gold_rows]
+    want = evalmetrics.image_eval(exact.exact_scores(q, c, eps=1e-6, dtype=torch.float32), keys, gold_keys)
+    corpus = m.ImageCorpus(feature_dict={k: c[i] for i, k in enumerate(keys)})
+    got = m.calculate_topk_accuracy_image_retrieval(corpus, q, gold_keys)
+    assert got == want, (got, want)
+    assert 0.2 < got[1] < 1.0 and got[10] >= got[1]
+
+
+def test_fp8_recall(m):
+    q, c = _data("text", 256, 768, 70), _data("text", 20000, 768, 71)
+    s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype="fp8", keep_source=False), 10, rescore_exact=False)
+    full8 = exact.exact_scores(q, c, operand="fp8")
+    assert exact.compare_topk(s, i, full8, 10, tie_tol=3e-6).ok                      # exact w.r.t. its own operands
+    want = exact.exact_topk(q, c, 10)[1]
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(i.cpu().tolist(), want.tolist())])
+    assert recall >= 0.80, recall
+    # with over-fetch + exact re-score the fp8 pass recovers the fp32 lists almost everywhere
+    s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype="fp8"), 10, overfetch=60)
+    recall2 = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(i.cpu().tolist(), want.tolist())])
+    assert recall2 >= 0.97, recall2
