@@ -125,9 +125,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Whole-cluster barrier.  The non-.aligned forms are used on purpose: the single-lane producer / MMA roles
+// leave their warps diverged, so callers __syncwarp() first and every thread then arrives on its own.
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared_cluster(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
 }
 
 // ---------------------------------------------------------------- TMA

@@ -38,9 +38,11 @@ namespace {
 constexpr int kTileM = 128;          // queries per tile  (UMMA M, TMEM lanes)
 constexpr int kTileN = 256;          // corpus rows per tile (UMMA N, TMEM columns)
 constexpr int kBlockKBytes = 128;    // one swizzle atom along K per stage
-constexpr int kABytes = kTileM * kBlockKBytes;   // 16 KB
-constexpr int kBBytes = kTileN * kBlockKBytes;   // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;   // 48 KB
+constexpr int kABytes = kTileM * kBlockKBytes;   // 16 KB of queries per CTA and stage
+// Corpus bytes per CTA and stage: the whole 256-row tile alone (32 KB), or half of it (16 KB) when two
+// CTAs of a pair run one cta_group::2 MMA over 256 queries x 256 corpus rows.
+__host__ __device__ constexpr int b_bytes(int cta) { return (kTileN / cta) * kBlockKBytes; }
+__host__ __device__ constexpr int stage_bytes(int cta) { return kABytes + b_bytes(cta); }
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
@@ -56,6 +58,7 @@ struct FusedParams {
   int kprime;            // list length kept per (query, strip)
   int stages;
   uint64_t* partial;     // [Q][S][kprime] keys
+  uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
   float* dense;          // dense mode: [Q][ldd] scores
   int64_t ldd;
   float out_scale;       // dense mode: multiplier applied to the accumulators
@@ -69,10 +72,10 @@ struct SmemLayout {
   uint32_t tmem_ptr_off;
   uint32_t total;        // including 1024 B of alignment slack
 };
-__host__ __device__ inline SmemLayout smem_layout(int stages, int cap) {
+__host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta) {
   SmemLayout l;
   l.stage_off = 0;
-  l.keys_off = stages * kStageBytes;
+  l.keys_off = stages * stage_bytes(cta);
   l.bars_off = l.keys_off + cap * 32 * 4 * 8;
   l.tmem_ptr_off = l.bars_off + (2 * kMaxStages + 4) * 8;
   l.total = l.tmem_ptr_off + 16 + 1024;
@@ -121,8 +124,9 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t (&k)[E], int lane) {
 }
 
 // Sort the candidate buffers of the rows named in `mask`; keep the best `kprime`.
-//   FINAL = false : write the survivors back, refresh the owner's count and threshold.
+//   FINAL = false : write the survivors back, refresh the owner's count.
 //   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
+// In both modes the owner lane's `thr` becomes the row's kprime-th best score once the row holds kprime entries.
 template <int CAP, bool FINAL>
 __device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int& cnt, float& thr,
                                              uint64_t* out_rows, int64_t out_row_stride) {
@@ -139,21 +143,12 @@ __device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int
       k[e] = (i < n) ? wkeys[key_slot_index(i, r)] : 0ull;
     }
     bitonic_sort_desc<E>(k, lane);
+    const int keep = n < kprime ? n : kprime;
     if constexpr (!FINAL) {
-      const int keep = n < kprime ? n : kprime;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
         if (i < keep) wkeys[key_slot_index(i, r)] = k[e];
-      }
-      const int last = kprime - 1;
-      uint64_t kk = k[0];
-#pragma unroll
-      for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[e] : kk;
-      kk = __shfl_sync(kFullMask, kk, last & 31);
-      if (lane == r) {
-        cnt = keep;
-        if (n >= kprime) thr = key_score(kk);
       }
     } else {
       uint64_t* out = out_rows + static_cast<int64_t>(r) * out_row_stride;
@@ -163,19 +158,44 @@ __device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int
         if (i < kprime) out[i] = k[e];   // empty slots are key 0
       }
     }
+    const int last = kprime - 1;
+    uint64_t kk = k[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[e] : kk;
+    kk = __shfl_sync(kFullMask, kk, last & 31);
+    if (lane == r) {
+      cnt = keep;
+      if (n >= kprime) thr = fmaxf(thr, key_score(kk));   // never below a bound learnt from other CTAs
+    }
   }
   __syncwarp();
 }
 
+// Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
+// value is the next float BELOW a row's current K-th best, so that "score > bound" still admits a score equal
+// to that K-th best (the (score desc, row asc) tie rule is decided later, by the sorts).  Any K-th best of a
+// subset of the corpus is a valid lower bound for the K-th best of the whole corpus.
+__device__ __forceinline__ void publish_threshold(uint32_t* thr_global, int64_t qrow, float thr) {
+  atomicMax(thr_global + qrow, float_to_ordered(thr) - 1u);
+}
+
 // ---------------------------------------------------------------- the kernel
-template <int CAP, bool kF8, bool kDense>
+// kCta = 1: one CTA per SM, UMMA 128 x 256.
+// kCta = 2: clusters of two CTAs (one TPC); the pair runs ONE tcgen05.mma.cta_group::2 of 256 queries x 256
+//           corpus rows per K step: each CTA stages its own 128 queries and HALF of the corpus tile, so the
+//           L2 -> shared-memory traffic per flop drops by a third and the smem operand reads per SM by a
+//           quarter.  CTA 0 (the leader) issues the MMAs; both CTAs own 128 accumulator rows in their TMEM.
+template <int CAP, bool kF8, bool kDense, int kCta>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                         const FusedParams p, const uint32_t idesc) {
+  constexpr int kStageBytes = stage_bytes(kCta);
+  constexpr int kUnitRows = kTileM * kCta;        // queries per unit (per CTA pair)
+  constexpr int kBRows = kTileN / kCta;           // corpus rows this CTA stages per tile
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024-byte alignment.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP);
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
@@ -185,64 +205,79 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCta == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = static_cast<int>(blockIdx.x) / kCta;          // first unit of this CTA (pair)
+  const int unit_stride = static_cast<int>(gridDim.x) / kCta;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);        // the leader's expect_tx arrival; TMA bytes of both CTAs complete it
+      mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_full[b], 1);       // one tcgen05.commit
+      mbar_init(&tmem_empty[b], 4 * kCta);   // one arrival per epilogue warp of every CTA of the pair
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<1>(tmem_ptr, kTmemCols);
+  if (warp == 1) tmem_alloc<kCta>(tmem_ptr, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int T = p.tiles_per_strip;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      // in a pair every CTA's bytes are counted on the LEADER's full barrier
+      uint32_t full_addr0 = smem_u32(&full_bar[0]);
+      if constexpr (kCta == 2) full_addr0 = mapa_shared_cluster(full_addr0, 0);
+      for (int u = unit0; u < p.n_units; u += unit_stride) {
         const int m_tile = u % p.n_m;
         const int strip = u / p.n_m;
         const int t0 = strip * T;
         const int t1 = min(t0 + T, p.n_n);
+        const int q_row = m_tile * kUnitRows + static_cast<int>(cta_rank) * kTileM;
         for (int t = t0; t < t1; ++t) {
+          const int c_row = t * kTileN + static_cast<int>(cta_rank) * kBRows;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
             uint8_t* sa = smem + L.stage_off + stage * kStageBytes;
             const int kelem = kb * (kF8 ? kBlockKBytes : kBlockKBytes / 2);
-            tma_load_2d(sa, &tmap_q, &full_bar[stage], kelem, m_tile * kTileM, kEvictLast);
-            tma_load_2d(sa + kABytes, &tmap_c, &full_bar[stage], kelem, t * kTileN, kEvictNormal);
+            if constexpr (kCta == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_2d(sa, &tmap_q, &full_bar[stage], kelem, q_row, kEvictLast);
+              tma_load_2d(sa + kABytes, &tmap_c, &full_bar[stage], kelem, c_row, kEvictNormal);
+            } else {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              const uint32_t bar = full_addr0 + stage * 8;
+              tma_load_2d_2sm(sa, &tmap_q, bar, kelem, q_row, kEvictLast);
+              tma_load_2d_2sm(sa + kABytes, &tmap_c, bar, kelem, c_row, kEvictNormal);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (single thread of the leader CTA)
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = unit0; u < p.n_units; u += unit_stride) {
         const int strip = u / p.n_m;
         const int t0 = strip * T;
         const int t1 = min(t0 + T, p.n_n);
         for (int t = t0; t < t1; ++t, ++it) {
           const uint32_t buf = it & 1;
-          mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, p.status, 2);
+          mbar_wait<kCta == 2>(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, p.status, 2);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kTileN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -254,12 +289,14 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int k = 0; k < kBlockKBytes / 32; ++k) {
               // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma<1, kF8>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma<kCta, kF8>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs retire
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if constexpr (kCta == 2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[buf]);         // accumulator complete -> epilogue
+          // accumulator complete -> epilogue warps (of both CTAs)
+          if constexpr (kCta == 2) umma_commit_2sm(&tmem_full[buf], 3); else umma_commit(&tmem_full[buf]);
         }
       }
     }
@@ -272,19 +309,28 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = unit0; u < p.n_units; u += unit_stride) {
       const int m_tile = u % p.n_m;
       const int strip = u / p.n_m;
       const int t0 = strip * T;
       const int t1 = min(t0 + T, p.n_n);
-      const int64_t qrow = static_cast<int64_t>(m_tile) * kTileM + row_in_tile;
+      const int64_t cta_row0 = static_cast<int64_t>(m_tile) * kUnitRows + static_cast<int64_t>(cta_rank) * kTileM;
+      const int64_t qrow = cta_row0 + row_in_tile;
       const bool valid = qrow < p.Q;
       float thr = valid ? kNegInf : kPosInf;
       int cnt = 0;
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1;
+        // pick up what other CTAs (and earlier strips) have learnt about this row while the MMAs finish
+        uint32_t shared_bound = 0u;
+        if constexpr (!kDense) {
+          if (valid) shared_bound = __ldcg(p.thr_global + qrow);
+        }
         mbar_wait(&tmem_full[buf], (it >> 1) & 1, p.status, 4);
         tc_fence_after();
+        if constexpr (!kDense) {
+          if (shared_bound != 0u) thr = fmaxf(thr, ordered_to_float(shared_bound));
+        }
         const int64_t col_tile = static_cast<int64_t>(t) * kTileN;
         const bool edge = col_tile + kTileN > p.N;
 #pragma unroll 1
@@ -293,9 +339,12 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
           tmem_ld_wait();
           if (c == kTileN / 32 - 1) {
-            // the whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
+            // the whole accumulator is in registers: hand the TMEM buffer back to the MMA issuer
             tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCta == 2) mbar_arrive_cluster(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
+            }
           }
           const int64_t col0 = col_tile + c * 32;
           float v[32];
@@ -314,14 +363,25 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               for (int j = 0; j < 32; ++j)
                 if (col0 + j >= p.N) v[j] = kNegInf;
             }
-            float m = v[0];
+            // max tree: four group maxima of 8 columns each, then the chunk maximum
+            float gm[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+            for (int g = 0; g < 4; ++g) {
+              const float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+              const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+              gm[g] = fmaxf(a, b);
+            }
+            const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
             if (__any_sync(kFullMask, m > thr)) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
+                if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
                 const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
-                if (need) compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                if (need) {
+                  const float before = thr;
+                  compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                  if (thr != before) publish_threshold(p.thr_global, qrow, thr);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float x = v[g * 8 + j];
@@ -338,20 +398,22 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if constexpr (!kDense) {
         // unit done: emit the sorted K-list of every valid row of this warp
         const uint32_t vmask = __ballot_sync(kFullMask, valid);
-        const int64_t row0 = static_cast<int64_t>(m_tile) * kTileM + quarter * 32;
+        const int64_t row0 = cta_row0 + quarter * 32;
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
+        const float before = thr;
         compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
                                 static_cast<int64_t>(p.n_strips) * p.kprime);
+        if (valid && thr != before) publish_threshold(p.thr_global, qrow, thr);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, kTmemCols);
+    tmem_dealloc<kCta>(tmem_base, kTmemCols);
   }
 }
 
@@ -399,9 +461,10 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int op_dtype, int64_
   return MMD_OK;
 }
 
+// Candidate-buffer capacity per query row.  A row is compacted back to kprime entries when fewer than 8 free
+// slots remain, so capacity - kprime is what amortises a compaction.
 int cap_for_k(int kprime) {
-  if (kprime <= 24) return 32;
-  if (kprime <= 56) return 64;
+  if (kprime <= 32) return 64;
   if (kprime <= 120) return 128;
   return 0;
 }
@@ -413,9 +476,11 @@ struct Schedule {
 // Pick the strip length.  Units are dealt round-robin to `sms` persistent CTAs; the cost of a schedule is
 // the busiest CTA's tile count plus a per-unit restart charge (list warm-up + final sort + the extra
 // strip the merge has to fold), expressed in tiles.  Fewer strips win ties.
-Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks) {
+Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks, int cta) {
   Schedule s{};
-  s.n_m = static_cast<int>(ceil_div(Q, kTileM));
+  sms /= cta;                                   // schedulable entities: CTAs, or CTA pairs
+  if (sms < 1) sms = 1;
+  s.n_m = static_cast<int>(ceil_div(Q, kTileM * cta));
   s.n_n = static_cast<int>(ceil_div(N, kTileN));
   const int max_parts = kprime > 0 ? 4096 / kprime : 4096;
   int s_max = s.n_n < max_parts ? s.n_n : max_parts;
@@ -453,9 +518,13 @@ Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks) {
   s.S = best_S;
   s.T = best_T;
   s.n_units = s.n_m * s.S;
-  s.grid = s.n_units < sms ? s.n_units : sms;
+  s.grid = (s.n_units < sms ? s.n_units : sms) * cta;
   return s;
 }
+
+// Two-CTA pairs pay off as soon as there is more than one 128-query tile; a single tile (the reference's
+// one-query-per-call pattern) keeps every SM busy on its own strip instead.
+int cta_mode_for(int64_t Q) { return Q > kTileM ? 2 : 1; }
 
 }  // namespace
 
@@ -489,11 +558,11 @@ struct Profile {
 } g_profile;
 constexpr size_t kMaxProfiled = 512;
 
-template <int CAP, bool kF8, bool kDense>
+template <int CAP, bool kF8, bool kDense, int kCta>
 int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams& p, uint32_t idesc, int grid,
                  cudaStream_t stream) {
-  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP);
-  auto kern = fused_score_topk_kernel<CAP, kF8, kDense>;
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta);
+  auto kern = fused_score_topk_kernel<CAP, kF8, kDense, kCta>;
   static bool attr_set = false;   // one per template instantiation
   if (!attr_set) {
     MMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -508,20 +577,45 @@ int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams
     }
   }
   if (profiled) cudaEventRecord(e0, stream);
-  kern<<<grid, kThreads, L.total, stream>>>(tq, tc, p, idesc);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tq, tc, p, idesc);
   if (profiled) {
     cudaEventRecord(e1, stream);
     std::lock_guard<std::mutex> g(g_profile.mu);
     g_profile.events.emplace_back(e0, e1);
   }
   count_launch();
+  MMD_CUDA_OK(le);
   MMD_CUDA_OK(cudaGetLastError());
   return MMD_OK;
 }
 
-int stages_for(int cap) {
+// op format x pair mode dispatch for one CAP
+template <int CAP, bool kDense>
+int launch_any(bool f8, int cta, const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams& p, uint32_t idesc,
+               int grid, cudaStream_t stream) {
+  if (cta == 2) {
+    return f8 ? launch_fused<CAP, true, kDense, 2>(tq, tc, p, idesc, grid, stream)
+              : launch_fused<CAP, false, kDense, 2>(tq, tc, p, idesc, grid, stream);
+  }
+  return f8 ? launch_fused<CAP, true, kDense, 1>(tq, tc, p, idesc, grid, stream)
+            : launch_fused<CAP, false, kDense, 1>(tq, tc, p, idesc, grid, stream);
+}
+
+int stages_for(int cap, int cta) {
   for (int st = kMaxStages; st >= 2; --st)
-    if (smem_layout(st, cap).total <= static_cast<uint32_t>(kMaxSmem)) return st;
+    if (smem_layout(st, cap, cta).total <= static_cast<uint32_t>(kMaxSmem)) return st;
   return 0;
 }
 
@@ -534,10 +628,10 @@ int sm_count() {
   return sms;
 }
 
-uint32_t idesc_for(int op_dtype) {
-  // kind::f16: 0 = f16, 1 = bf16 ; kind::f8f6f4: 0 = e4m3
+uint32_t idesc_for(int op_dtype, int cta) {
+  // kind::f16: 0 = f16, 1 = bf16 ; kind::f8f6f4: 0 = e4m3.  A pair's MMA spans 256 query rows.
   const uint32_t fmt = (op_dtype == MMD_OP_BF16 || op_dtype == MMD_OP_BF16X3) ? 1u : 0u;
-  return make_idesc(fmt, kTileM, kTileN);
+  return make_idesc(fmt, kTileM * cta, kTileN);
 }
 
 }  // namespace
@@ -576,8 +670,8 @@ extern "C" size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op
   // exactly what mmd_topk_scores will carve up: one K-list per (query, strip) of the planned schedule
   PreparedLayout lay;
   if (!prepared_layout(op_dtype, dim, &lay)) return 0;
-  const Schedule sch = plan_schedule(Q, N, k, sm_count(), static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)));
-  return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + 256;
+  const Schedule sch = plan_schedule(Q, N, k, sm_count(), static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)), cta_mode_for(Q));
+  return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + static_cast<size_t>(Q) * sizeof(uint32_t) + 256;
 }
 
 extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
@@ -606,8 +700,10 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_topk_scores: bad op_dtype %d", op_dtype);
 
   const int sms = sm_count();
-  const Schedule sch = plan_schedule(Q, N, k, sms, static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)));
-  const size_t need = static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t);
+  const int cta = cta_mode_for(Q);
+  const Schedule sch = plan_schedule(Q, N, k, sms, static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)), cta);
+  const size_t keys_bytes = static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t);
+  const size_t need = keys_bytes + static_cast<size_t>(Q) * sizeof(uint32_t);
   if (workspace == nullptr || workspace_bytes < need) {
     set_last_error("mmd_topk_scores: workspace %zu < %zu bytes", workspace_bytes, need);
     return MMD_ERR_WORKSPACE;
@@ -617,7 +713,7 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   CUtensorMap tq, tc;
   rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, kTileM);
   if (rc != MMD_OK) return rc;
-  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN);
+  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN / cta);
   if (rc != MMD_OK) return rc;
 
   FusedParams p{};
@@ -625,16 +721,17 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = sch.T; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = k;
-  p.stages = stages_for(cap);
+  p.stages = stages_for(cap, cta);
   p.partial = static_cast<uint64_t*>(workspace);
+  p.thr_global = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + keys_bytes);
+  MMD_CUDA_OK(cudaMemsetAsync(p.thr_global, 0, static_cast<size_t>(Q) * sizeof(uint32_t), st));
   p.dense = nullptr; p.ldd = 0; p.out_scale = 1.0f;
   p.status = device_status_word();
-  const uint32_t idesc = idesc_for(op_dtype);
+  const uint32_t idesc = idesc_for(op_dtype, cta);
   const bool f8 = op_dtype == MMD_OP_E4M3;
 
-  if (cap == 32) rc = f8 ? launch_fused<32, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<32, false, false>(tq, tc, p, idesc, sch.grid, st);
-  else if (cap == 64) rc = f8 ? launch_fused<64, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<64, false, false>(tq, tc, p, idesc, sch.grid, st);
-  else rc = f8 ? launch_fused<128, true, false>(tq, tc, p, idesc, sch.grid, st) : launch_fused<128, false, false>(tq, tc, p, idesc, sch.grid, st);
+  if (cap == 64) rc = launch_any<64, false>(f8, cta, tq, tc, p, idesc, sch.grid, st);
+  else rc = launch_any<128, false>(f8, cta, tq, tc, p, idesc, sch.grid, st);
   if (rc != MMD_OK) return rc;
 
   const float scale = f8 ? (1.0f / 65536.0f) : 1.0f;
@@ -655,16 +752,17 @@ extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_d
   PreparedLayout lay;
   MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_scores_dense: bad op_dtype %d", op_dtype);
   const int sms = sm_count();
+  const int cta = cta_mode_for(Q);
   Schedule sch{};
-  sch.n_m = static_cast<int>(ceil_div(Q, kTileM));
+  sch.n_m = static_cast<int>(ceil_div(Q, kTileM * cta));
   sch.n_n = static_cast<int>(ceil_div(N, kTileN));
   sch.T = 1; sch.S = sch.n_n; sch.n_units = sch.n_m * sch.S;
-  sch.grid = sch.n_units < sms ? sch.n_units : sms;
+  sch.grid = (sch.n_units < sms / cta ? sch.n_units : sms / cta) * cta;
 
   CUtensorMap tq, tc;
   rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, kTileM);
   if (rc != MMD_OK) return rc;
-  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN);
+  rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN / cta);
   if (rc != MMD_OK) return rc;
 
   FusedParams p{};
@@ -672,14 +770,14 @@ extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_d
   p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = 1; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = 0;
-  p.stages = stages_for(0);
-  if (p.stages > 4) p.stages = 4;
+  p.stages = stages_for(0, cta);
+  if (p.stages > 6) p.stages = 6;
   p.partial = nullptr;
+  p.thr_global = nullptr;
   p.dense = out_scores; p.ldd = ld_scores;
   const bool f8 = op_dtype == MMD_OP_E4M3;
   p.out_scale = f8 ? (1.0f / 65536.0f) : 1.0f;
   p.status = device_status_word();
-  const uint32_t idesc = idesc_for(op_dtype);
-  return f8 ? launch_fused<32, true, true>(tq, tc, p, idesc, sch.grid, st)
-            : launch_fused<32, false, true>(tq, tc, p, idesc, sch.grid, st);
+  const uint32_t idesc = idesc_for(op_dtype, cta);
+  return launch_any<64, true>(f8, cta, tq, tc, p, idesc, sch.grid, st);
 }
