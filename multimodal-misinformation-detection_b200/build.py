@@ -49,6 +49,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("MMD_STATS"):
+        extra.append("-DMMD_STATS")      # developer build: wait-cycle counters in the fused kernel
 
     def compile_one(src: str) -> Path:
         obj = OBJ_DIR / (Path(src).stem + ".o")

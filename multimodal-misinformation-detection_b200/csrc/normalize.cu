@@ -120,7 +120,10 @@ __device__ __forceinline__ void store8(uint8_t* __restrict__ dst_row, int g, int
   }
 }
 
-template <typename T, int OP, bool kVec>
+// G = number of 8-value groups each lane keeps in registers (row length <= 256 * G values); kTail = the row
+// is longer than that and the rest is streamed twice.  Small G keeps the register count low, so more warps
+// (and more 128-bit loads) are in flight per SM -- this kernel lives on memory-level parallelism.
+template <typename T, int OP, bool kVec, int G, bool kTail>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t src_stride, int normalize,
                       float eps, int side, uint8_t* __restrict__ dst, int64_t dpad, int64_t row_bytes,
@@ -134,22 +137,29 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
     const T* __restrict__ row = src + r * src_stride;
     uint8_t* __restrict__ drow = dst + r * row_bytes;
 
-    float cache[kMaxCachedGroups][8];
-    float ss = 0.0f;
+    float cache[G][8];
 #pragma unroll
-    for (int i = 0; i < kMaxCachedGroups; ++i) {
+    for (int i = 0; i < G; ++i) {          // all loads first: G (x2 for fp32) independent 128-bit requests per lane
       const int g = lane + 32 * i;
       if (g < n_groups) {
         load8<T, kVec>(row, g, dim, cache[i]);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(cache[i][j], cache[i][j], ss);
+        for (int j = 0; j < 8; ++j) cache[i][j] = 0.0f;
       }
     }
-    for (int g = lane + 32 * kMaxCachedGroups; g < n_groups; g += 32) {
-      float v[8];
-      load8<T, kVec>(row, g, dim, v);
+    float ss = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(cache[i][j], cache[i][j], ss);
+    if constexpr (kTail) {
+      for (int g = lane + 32 * G; g < n_groups; g += 32) {
+        float v[8];
+        load8<T, kVec>(row, g, dim, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+      }
     }
     float denom = 1.0f;
     if (normalize) {
@@ -160,7 +170,7 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
     if (lane == 0 && inv_norm != nullptr) inv_norm[r] = 1.0f / denom;
 
 #pragma unroll
-    for (int i = 0; i < kMaxCachedGroups; ++i) {
+    for (int i = 0; i < G; ++i) {
       const int g = lane + 32 * i;
       if (g < n_groups) {
         float y[8];
@@ -169,14 +179,35 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
         store8<OP>(drow, g, dpad, side, y);
       }
     }
-    for (int g = lane + 32 * kMaxCachedGroups; g < n_groups; g += 32) {
-      float v[8];
-      load8<T, kVec>(row, g, dim, v);
+    if constexpr (kTail) {
+      for (int g = lane + 32 * G; g < n_groups; g += 32) {
+        float v[8];
+        load8<T, kVec>(row, g, dim, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = normalize ? v[j] / denom : v[j];
-      store8<OP>(drow, g, dpad, side, v);
+        for (int j = 0; j < 8; ++j) v[j] = normalize ? v[j] / denom : v[j];
+        store8<OP>(drow, g, dpad, side, v);
+      }
     }
   }
+}
+
+template <typename T, int OP, bool kVec, int G, bool kTail>
+void launch_g(unsigned grid, cudaStream_t stream, const T* s, int64_t rows, int dim, int64_t src_stride, int normalize,
+              float eps, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
+  normalize_cast_kernel<T, OP, kVec, G, kTail><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+      s, rows, dim, src_stride, normalize, eps, side, d, lay.dpad, lay.row_bytes, inv_norm);
+}
+
+template <typename T, int OP, bool kVec>
+void launch_v(unsigned grid, cudaStream_t stream, const T* s, int64_t rows, int dim, int64_t src_stride, int normalize,
+              float eps, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
+  const int per_lane = static_cast<int>(ceil_div(lay.dpad / 8, 32));
+  if (per_lane <= 1) launch_g<T, OP, kVec, 1, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else if (per_lane <= 2) launch_g<T, OP, kVec, 2, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else if (per_lane <= 3) launch_g<T, OP, kVec, 3, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else if (per_lane <= 4) launch_g<T, OP, kVec, 4, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else if (per_lane <= kMaxCachedGroups) launch_g<T, OP, kVec, kMaxCachedGroups, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else launch_g<T, OP, kVec, kMaxCachedGroups, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
 }
 
 template <typename T, int OP>
@@ -187,17 +218,12 @@ int launch(const void* src, int64_t rows, int dim, int64_t src_stride, int norma
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = ceil_div(rows, kWarpsPerBlock);
-  const int64_t cap = static_cast<int64_t>(sms) * 8 * 4;  // a few waves of 8 resident CTAs per SM, grid-stride beyond
+  const int64_t cap = static_cast<int64_t>(sms) * 8 * 8;  // several waves of resident CTAs per SM, grid-stride beyond
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   auto* s = static_cast<const T*>(src);
   auto* d = static_cast<uint8_t*>(dst);
-  if (vec) {
-    normalize_cast_kernel<T, OP, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        s, rows, dim, src_stride, normalize, eps, side, d, lay.dpad, lay.row_bytes, inv_norm);
-  } else {
-    normalize_cast_kernel<T, OP, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        s, rows, dim, src_stride, normalize, eps, side, d, lay.dpad, lay.row_bytes, inv_norm);
-  }
+  if (vec) launch_v<T, OP, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  else launch_v<T, OP, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
   count_launch();
   MMD_CUDA_OK(cudaGetLastError());
   return MMD_OK;

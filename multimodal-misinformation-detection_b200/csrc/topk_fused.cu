@@ -21,6 +21,7 @@
 // Every unit leaves a sorted K-list per query; topk_merge.cu folds the strips together.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -63,7 +64,19 @@ struct FusedParams {
   int64_t ldd;
   float out_scale;       // dense mode: multiplier applied to the accumulators
   DeviceStatus* status;
+  unsigned long long* stats;   // developer builds (-DMMD_STATS): per-CTA wait-cycle counters, else unused
 };
+
+#ifdef MMD_STATS
+// developer timeline: block 0 records clock64() at a few points of every tile (up to 128 tiles):
+//   stats[tile*8 + 0] MMA: before tmem_empty wait   [1] MMA: after wait   [2] MMA: all MMAs of the tile issued
+//   stats[tile*8 + 4] EPI(warp 2): before tmem_full wait   [5] after wait   [6] tile processed
+#define MMD_TRACE(tile, slot) do { if (p.stats && blockIdx.x == 0 && (tile) < 128) p.stats[(tile) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define MMD_TRACE(tile, slot) do { } while (0)
+#endif
+#define MMD_STAT_BEGIN() do { } while (0)
+#define MMD_STAT_END(slot) do { } while (0)
 
 struct SmemLayout {
   uint32_t stage_off;    // stages x {A,B}
@@ -247,7 +260,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int t = t0; t < t1; ++t) {
           const int c_row = t * kTileN + static_cast<int>(cta_rank) * kBRows;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1);
+            { MMD_STAT_BEGIN(); mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1); MMD_STAT_END(0); }
             uint8_t* sa = smem + L.stage_off + stage * kStageBytes;
             const int kelem = kb * (kF8 ? kBlockKBytes : kBlockKBytes / 2);
             if constexpr (kCta == 1) {
@@ -277,11 +290,13 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int t1 = min(t0 + T, p.n_n);
         for (int t = t0; t < t1; ++t, ++it) {
           const uint32_t buf = it & 1;
+          MMD_TRACE(it, 0);
           mbar_wait<kCta == 2>(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, p.status, 2);
+          MMD_TRACE(it, 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kTileN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase, p.status, 3);
+            { MMD_STAT_BEGIN(); mbar_wait(&full_bar[stage], phase, p.status, 3); MMD_STAT_END(2); }
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + L.stage_off + stage * kStageBytes);
             const uint64_t adesc = make_smem_desc_sw128(sa);
@@ -297,6 +312,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
           // accumulator complete -> epilogue warps (of both CTAs)
           if constexpr (kCta == 2) umma_commit_2sm(&tmem_full[buf], 3); else umma_commit(&tmem_full[buf]);
+          MMD_TRACE(it, 2);
         }
       }
     }
@@ -326,7 +342,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if constexpr (!kDense) {
           if (valid) shared_bound = __ldcg(p.thr_global + qrow);
         }
+        if (warp == 2 && lane == 0) MMD_TRACE(it, 4);
         mbar_wait(&tmem_full[buf], (it >> 1) & 1, p.status, 4);
+        if (warp == 2 && lane == 0) MMD_TRACE(it, 5);
         tc_fence_after();
         if constexpr (!kDense) {
           if (shared_bound != 0u) thr = fmaxf(thr, ordered_to_float(shared_bound));
@@ -394,6 +412,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
         }
+        if (warp == 2 && lane == 0) MMD_TRACE(it, 6);
       }
       if constexpr (!kDense) {
         // unit done: emit the sorted K-list of every valid row of this warp
@@ -524,7 +543,11 @@ Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks, i
 
 // Two-CTA pairs pay off as soon as there is more than one 128-query tile; a single tile (the reference's
 // one-query-per-call pattern) keeps every SM busy on its own strip instead.
-int cta_mode_for(int64_t Q) { return Q > kTileM ? 2 : 1; }
+int cta_mode_for(int64_t Q) {
+  static const int forced = [] { const char* e = getenv("MMD_CTA_MODE"); return e ? atoi(e) : 0; }();   // tuning knob
+  if (forced == 1 || forced == 2) return forced;
+  return Q > kTileM ? 2 : 1;
+}
 
 }  // namespace
 
@@ -614,6 +637,8 @@ int launch_any(bool f8, int cta, const CUtensorMap& tq, const CUtensorMap& tc, c
 }
 
 int stages_for(int cap, int cta) {
+  static const int forced = [] { const char* e = getenv("MMD_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
+  if (forced >= 2 && forced <= kMaxStages && smem_layout(forced, cap, cta).total <= static_cast<uint32_t>(kMaxSmem)) return forced;
   for (int st = kMaxStages; st >= 2; --st)
     if (smem_layout(st, cap, cta).total <= static_cast<uint32_t>(kMaxSmem)) return st;
   return 0;
@@ -727,6 +752,24 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   MMD_CUDA_OK(cudaMemsetAsync(p.thr_global, 0, static_cast<size_t>(Q) * sizeof(uint32_t), st));
   p.dense = nullptr; p.ldd = 0; p.out_scale = 1.0f;
   p.status = device_status_word();
+  p.stats = nullptr;
+#ifdef MMD_STATS
+  {
+    static unsigned long long* dstats = nullptr;
+    static int calls = 0;
+    if (dstats == nullptr) { cudaMalloc(&dstats, 1024 * sizeof(unsigned long long)); cudaMemset(dstats, 0, 1024 * 8); }
+    if (++calls == 4) {          // dump the timeline of the previous (warm) launch once
+      unsigned long long h[1024];
+      cudaMemcpy(h, dstats, sizeof(h), cudaMemcpyDeviceToHost);
+      const unsigned long long t0 = h[0];
+      for (int t = 0; t < 128 && h[t * 8 + 2] != 0; ++t)
+        fprintf(stderr, "[trace] tile %3d  mma: start %8lld waited %6lld issue-done %8lld | epi: wait-start %8lld got %8lld done %8lld\n", t,
+                (long long)(h[t * 8] - t0), (long long)(h[t * 8 + 1] - h[t * 8]), (long long)(h[t * 8 + 2] - t0),
+                (long long)(h[t * 8 + 4] - t0), (long long)(h[t * 8 + 5] - t0), (long long)(h[t * 8 + 6] - t0));
+    }
+    p.stats = dstats;
+  }
+#endif
   const uint32_t idesc = idesc_for(op_dtype, cta);
   const bool f8 = op_dtype == MMD_OP_E4M3;
 
@@ -774,6 +817,7 @@ extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_d
   if (p.stages > 6) p.stages = 6;
   p.partial = nullptr;
   p.thr_global = nullptr;
+  p.stats = nullptr;
   p.dense = out_scores; p.ldd = ld_scores;
   const bool f8 = op_dtype == MMD_OP_E4M3;
   p.out_scale = f8 ? (1.0f / 65536.0f) : 1.0f;

@@ -11,7 +11,7 @@ import threading
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmmd.so"
+LIB_PATH = Path(os.environ["MMD_LIB_PATH"]) if os.environ.get("MMD_LIB_PATH") else _HERE / "libmmd.so"   # override: developer builds
 
 MMD_OK = 0
 SRC_F32, SRC_F16, SRC_BF16 = 0, 1, 2

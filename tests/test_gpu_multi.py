@@ -1,0 +1,59 @@
+"""GPU, >= 2 devices on one box: the row-sharded path with NCCL (one process per GPU) against the CPU oracle.
+Skipped on a single-GPU box (tests/test_gpu_parity.py::test_sharded_equals_unsharded covers the shard-invariance
+of the kernels there, tests/test_sharded_gloo.py the collective plumbing)."""
+import os
+import socket
+
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import mmd_retrieval as m
+    from oracle import exact
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        gen = torch.Generator().manual_seed(99)
+        corpus = torch.randn(30011, 768, generator=gen)
+        corpus[30010] = corpus[5]                              # duplicate rows on different ranks
+        queries = torch.randn(300, 768, generator=gen)
+        queries[0] = corpus[5] * 2
+        sc = m.ShardedCorpus.from_full(corpus.cuda())
+        s, i = sc.topk(queries.cuda(), 10)
+        full = exact.exact_scores(queries, corpus)
+        cmp = exact.compare_topk(s, i, full, 10, tie_tol=2e-6)
+        assert cmp.ok and cmp.max_rel_score_err <= 1e-5, cmp
+        assert i[0, :2].tolist() == [5, 30010]
+        # host queries in, the public call moves them
+        s2, i2 = sc.topk(queries, 10)
+        assert torch.equal(i2, i)
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_topk_nccl():
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out.get(r) for r in range(world))

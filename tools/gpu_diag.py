@@ -145,7 +145,31 @@ def stage_perf():
         print(f"perf Q={Q} N={N} D={D} k={k}: step {ms:.3f} ms ({Q/ms*1e3:.0f} q/s); fused kernel {fm:.3f} ms = {fl/fm/1e9:.0f} TFLOP/s")
 
 
-STAGES = {"k1": stage_k1, "dense1": stage_dense1, "dense2": stage_dense2, "topk": stage_topk, "perf": stage_perf}
+def stage_k1perf():
+    import torch
+    import mmd_retrieval as m
+    from mmd_retrieval import _lib
+    for (rows, dim, sdt, op) in [(1_000_000, 768, torch.float32, "bf16"), (1_000_000, 768, torch.float16, "bf16"),
+                                 (200_000, 2048, torch.float32, "bf16"), (1_000_000, 768, torch.float32, "fp8"),
+                                 (16384, 768, torch.float32, "bf16"), (300_000, 768, torch.float32, "fp32")]:
+        x = torch.randn(rows, dim, device="cuda").to(sdt)
+        for _ in range(2):
+            m.normalize_cast(x, op, _lib.SIDE_CORPUS, True, 1e-12)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            out, inv = m.normalize_cast(x, op, _lib.SIDE_CORPUS, True, 1e-12)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        by = x.numel() * x.element_size() + out.numel() + inv.numel() * 4
+        print(f"k1perf rows={rows} dim={dim} src={sdt} op={op}: {ms:.3f} ms, {by/ms/1e6:.0f} GB/s (incl. allocator)")
+        del x, out
+
+
+STAGES = {"k1perf": stage_k1perf, "k1": stage_k1, "dense1": stage_dense1, "dense2": stage_dense2, "topk": stage_topk, "perf": stage_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--run":

@@ -1,0 +1,14 @@
+"""Developer tool: run one workload a few times with the MMD_STATS build to dump the per-tile timeline."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-misinformation-detection_b200"))
+import torch
+import mmd_retrieval as m
+Q, N, D, k = [int(x) for x in sys.argv[1:5]]
+g = torch.Generator(device="cuda").manual_seed(1)
+q = torch.randn(Q, D, device="cuda", generator=g)
+c = torch.randn(N, D, device="cuda", generator=g)
+pc = m.prepare_corpus(c, dtype="bf16", keep_source=False)
+for _ in range(5):
+    m.topk(q, pc, k, rescore_exact=False)
+torch.cuda.synchronize()
