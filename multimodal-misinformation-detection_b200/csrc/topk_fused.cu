@@ -184,6 +184,28 @@ __device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int
   __syncwarp();
 }
 
+// Per-thread bitonic sort (descending) of a small register array; all indices are compile-time constants.
+template <int N>
+__device__ __forceinline__ void thread_sort_desc(float (&v)[N]) {
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const float a = v[i], b = v[j];
+          const float mx = fmaxf(a, b), mn = fminf(a, b);
+          v[i] = desc ? mx : mn;
+          v[j] = desc ? mn : mx;
+        }
+      }
+    }
+  }
+}
+
 // Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
 // value is the next float BELOW a row's current K-th best, so that "score > bound" still admits a score equal
 // to that K-th best (the (score desc, row asc) tie rule is decided later, by the sorts).  Any K-th best of a
@@ -351,6 +373,40 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         const int64_t col_tile = static_cast<int64_t>(t) * kTileN;
         const bool edge = col_tile + kTileN > p.N;
+        if constexpr (!kDense && CAP == 64) {
+          // Cold start: a row about which nothing is known yet (thr = -inf) would push every score of its first
+          // tile through the candidate buffer (one warp-wide sort per ~40 scores).  Instead, read the tile once
+          // more: the K'-th largest of its 32 group maxima (8 columns each) is K' distinct scores of this row,
+          // hence a lower bound of the row's K'-th best; it admits ~8 % of the tile.
+          if (__any_sync(kFullMask, valid && thr == kNegInf)) {
+            float gmx[32];
+#pragma unroll
+            for (int c = 0; c < kTileN / 32; ++c) {
+              uint32_t raw[32];
+              tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float mx = kNegInf;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float x = __uint_as_float(raw[8 * g + j]);
+                  const bool in_range = !edge || (col_tile + c * 32 + 8 * g + j < p.N);
+                  mx = in_range ? fmaxf(mx, x) : mx;
+                }
+                gmx[4 * c + g] = (mx == mx) ? mx : kNegInf;
+              }
+            }
+            thread_sort_desc<32>(gmx);
+            float kth = gmx[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) kth = (i == p.kprime - 1) ? gmx[i] : kth;
+            if (valid && thr == kNegInf && kth > kNegInf) {
+              publish_threshold(p.thr_global, qrow, kth);
+              thr = ordered_to_float(float_to_ordered(kth) - 1u);     // admit scores equal to the bound
+            }
+          }
+        }
 #pragma unroll 1
         for (int c = 0; c < kTileN / 32; ++c) {
           uint32_t raw[32];

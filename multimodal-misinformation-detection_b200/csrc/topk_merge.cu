@@ -6,8 +6,12 @@
 // inside sentence_transformers.util.semantic_search (call sites src/evidence/text2text_retrieval.py:56-64),
 // and the list concat + sort of src/evidence/text2text_retrieval.py:97-110.
 //
-// One query per warp (<= 128 candidates, shuffle bitonic sort in registers) or per 256-thread block
-// (<= 4096 candidates, bitonic sort in shared memory).  Order: (score descending, row ascending).
+// Lists of up to 128 entries (every list the fused kernel produces): one query per warp keeps a running sorted
+// list in registers and folds one partial list at a time into it -- max against the reversed newcomer (the
+// bitonic half-cleaner: the result holds the best 32*E of both) plus one log2-depth bitonic merge through
+// shuffles.  O(parts * log L) per query instead of a full sort of parts * k_in keys.  Longer lists: one query
+// per 256-thread block, bitonic sort in shared memory (<= 4096 candidates).
+// Order: (score descending, row ascending).
 #include "common.cuh"
 
 namespace mmd {
@@ -95,6 +99,79 @@ merge_warp_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, floa
   for (int i = 32 * E + lane; i < k_out; i += 32) store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
 }
 
+// Bitonic merge network: `k` holds a bitonic sequence over i = e * 32 + lane; afterwards it is descending in i.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_merge_desc(uint64_t (&k)[E], int lane) {
+#pragma unroll
+  for (int stride = 16 * E; stride > 0; stride >>= 1) {
+    if (stride >= 32) {
+      const int es = stride >> 5;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & es) == 0) {
+          const uint64_t a = k[e], b = k[e | es];
+          k[e] = a > b ? a : b;
+          k[e | es] = a > b ? b : a;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint64_t other = __shfl_xor_sync(kFull, k[e], stride);
+        const bool lower = (lane & stride) == 0;
+        const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
+        k[e] = lower ? mx : mn;
+      }
+    }
+  }
+}
+
+// Streaming merge, one query per warp, lists of at most L = 32 * E entries.
+//   kSortedParts = true : every partial list is already descending (the fused kernel's strips).
+//   kSortedParts = false: partial lists in any order (caller-provided lists): each is sorted first.
+template <int E, bool kSortedParts>
+__global__ void __launch_bounds__(128)
+merge_stream_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, float* __restrict__ out_s,
+                    int32_t* __restrict__ out_i) {
+  constexpr int L = 32 * E;
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (q >= src.Q) return;
+  uint64_t best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = 0ull;
+  for (int part = 0; part < src.parts; ++part) {
+    uint64_t nw[E];
+    if constexpr (kSortedParts) {
+      // position i of the ascending newcomer = entry L-1-i of the descending list (empty slots first)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = L - 1 - (e * 32 + lane);
+        nw[e] = j < src.k_in ? load_candidate(src, q, part * src.k_in + j) : 0ull;
+      }
+    } else {
+      uint64_t tmp[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = e * 32 + lane;
+        tmp[e] = j < src.k_in ? load_candidate(src, q, part * src.k_in + j) : 0ull;
+      }
+      warp_bitonic_desc<E>(tmp, lane);
+#pragma unroll
+      for (int e = 0; e < E; ++e) nw[e] = __shfl_sync(kFull, tmp[E - 1 - e], 31 - lane);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) best[e] = best[e] > nw[e] ? best[e] : nw[e];
+    warp_bitonic_merge_desc<E>(best, lane);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < k_out) store_result(best[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+  }
+  for (int i = L + lane; i < k_out; i += 32) store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+}
+
 template <int L>
 __global__ void __launch_bounds__(256)
 merge_block_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, float* __restrict__ out_s,
@@ -119,20 +196,22 @@ merge_block_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, flo
     store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
 }
 
+template <bool kSortedParts>
 int launch_merge(const MergeSrc& src, int k_out, float scale, int64_t idx_offset, float* out_s, int32_t* out_i,
                  cudaStream_t stream) {
   const int total = src.parts * src.k_in;
   const unsigned qblocks = static_cast<unsigned>(ceil_div(src.Q, 4));
-  if (total <= 32) merge_warp_kernel<1><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
-  else if (total <= 64) merge_warp_kernel<2><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
-  else if (total <= 128) merge_warp_kernel<4><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  const int longest = src.k_in > k_out ? src.k_in : k_out;
+  if (longest <= 32) merge_stream_kernel<1, kSortedParts><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (longest <= 64) merge_stream_kernel<2, kSortedParts><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
+  else if (longest <= 128) merge_stream_kernel<4, kSortedParts><<<qblocks, 128, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else if (total <= 256) merge_block_kernel<256><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else if (total <= 512) merge_block_kernel<512><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else if (total <= 1024) merge_block_kernel<1024><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else if (total <= 2048) merge_block_kernel<2048><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else if (total <= 4096) merge_block_kernel<4096><<<static_cast<unsigned>(src.Q), 256, 0, stream>>>(src, k_out, scale, idx_offset, out_s, out_i);
   else {
-    set_last_error("merge: %d candidates per query exceeds 4096", total);
+    set_last_error("merge: %d candidates per query exceeds 4096 (lists longer than 128 entries)", total);
     return MMD_ERR_ARG;
   }
   count_launch();
@@ -155,7 +234,7 @@ int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, 
     // no candidates at all: make load_candidate return "empty" for every slot
     src.keys = reinterpret_cast<const uint64_t*>(out_scores);   // never dereferenced (parts == 0)
   }
-  return launch_merge(src, k_out, scale, idx_offset, out_scores, out_idx, stream);
+  return launch_merge<true>(src, k_out, scale, idx_offset, out_scores, out_idx, stream);
 }
 
 }  // namespace mmd
@@ -168,8 +247,8 @@ extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts
   if (Q == 0) return MMD_OK;
   MMD_REQUIRE(scores != nullptr && idx != nullptr && out_scores != nullptr && out_idx != nullptr,
               "mmd_topk_merge: null buffer");
-  MMD_REQUIRE(static_cast<int64_t>(parts) * k_in <= 4096, "mmd_topk_merge: parts*k_in = %lld exceeds 4096",
-              (long long)parts * k_in);
+  MMD_REQUIRE((k_in <= 128 && k_out <= 128) || static_cast<int64_t>(parts) * k_in <= 4096,
+              "mmd_topk_merge: parts*k_in = %lld exceeds 4096 (only lists of <= 128 entries stream)", (long long)parts * k_in);
   MMD_REQUIRE(k_out <= 4096, "mmd_topk_merge: k_out %d exceeds 4096", k_out);
   int rc = mmd_device_check();
   if (rc != MMD_OK) return rc;
@@ -180,5 +259,5 @@ extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts
   src.parts = parts;
   src.k_in = k_in;
   src.Q = Q;
-  return launch_merge(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+  return launch_merge<false>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
 }

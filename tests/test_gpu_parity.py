@@ -262,7 +262,8 @@ def test_edge_cases(m):
 # ------------------------------------------------------------------------------------------ K3b / K4 / K5
 def test_merge_kernel(m):
     gen = torch.Generator().manual_seed(40)
-    for parts, n_q, k_in, k_out in [(2, 50, 10, 10), (8, 33, 100, 100), (3, 7, 5, 12), (37, 9, 18, 18), (1, 4, 4, 2)]:
+    for parts, n_q, k_in, k_out in [(2, 50, 10, 10), (8, 33, 100, 100), (3, 7, 5, 12), (37, 9, 18, 18), (1, 4, 4, 2),
+                                      (40, 5, 120, 64), (3, 6, 200, 130), (64, 3, 100, 100)]:
         s = torch.randn(parts, n_q, k_in, generator=gen).round(decimals=1)       # plenty of equal scores
         idx = torch.stack([torch.stack([torch.randperm(1000, generator=gen)[:k_in] for _ in range(n_q)]) + 1000 * p
                            for p in range(parts)]).to(torch.int32)

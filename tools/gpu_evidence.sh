@@ -1,0 +1,45 @@
+#!/usr/bin/env bash
+# One gpurun call that produces the round's evidence under gpurun_out/<tag>/:
+#   GPU parity tests, smoke(), the bench line (ours + reference arm), the ncu launch list and the
+#   `--set full` captures of the fused kernel (C3 and C2 shapes) and of K1.
+# Usage (from the repo root, on the GPU box):  bash tools/gpu_evidence.sh <tag> [quick]
+set -u
+TAG=${1:-r1}
+QUICK=${2:-}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > "$OUT/gpu.csv" 2>&1
+
+python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+echo "pytest rc=$?" | tee -a "$OUT/pytest_gpu.log"
+python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1
+echo "smoke rc=$?" | tee -a "$OUT/smoke.log"
+
+python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"
+echo "bench rc=$?"
+tail -c 600 "$OUT/bench_n1.json"
+if [ -z "$QUICK" ]; then
+  python bench.py --impl reference --steps 1 --warmup 0 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
+  echo "ref rc=$?"
+fi
+
+SHORT="--steps 2 --warmup 1 --no-cpu-baseline --no-extra"
+# launch list of one short run (shares, not absolutes)
+python bench.py $SHORT > "$OUT/plain_c3.log" 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_c3.csv" \
+    python bench.py $SHORT > "$OUT/ncu_launches.log" 2>&1
+# full capture of the dominant kernel, C3 shape
+python bench.py $SHORT > "$OUT/plain_c3b.log" 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:fused_score_topk -s 1 -c 2 -f -o "$OUT/prof_c3_fused" \
+    python bench.py $SHORT > "$OUT/ncu_c3_fused.log" 2>&1
+if [ -z "$QUICK" ]; then
+  # C2 shape
+  python bench.py $SHORT --workload c2 > "$OUT/plain_c2.log" 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:fused_score_topk -s 1 -c 2 -f -o "$OUT/prof_c2_fused" \
+      python bench.py $SHORT --workload c2 > "$OUT/ncu_c2_fused.log" 2>&1
+  # K1 (corpus prepare is the first normalize_cast launch) + rescore + merge
+  python bench.py $SHORT > "$OUT/plain_c3c.log" 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"normalize_cast|rescore|merge" -c 6 -f -o "$OUT/prof_c3_aux" \
+      python bench.py $SHORT > "$OUT/ncu_c3_aux.log" 2>&1
+fi
+ls -la "$OUT"
