@@ -47,12 +47,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Arrive on the barrier at the same smem offset in CTA `cta` of the cluster.
+// Relaxed on purpose: the only thing the arrival hands over is a TMEM buffer whose tcgen05.ld reads have
+// already completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it).  A .release.cluster
+// arrive compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR and cost ~1.8k cycles per tile (ncu source page, r1b).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");

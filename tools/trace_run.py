@@ -6,8 +6,11 @@ import torch
 import mmd_retrieval as m
 Q, N, D, k = [int(x) for x in sys.argv[1:5]]
 g = torch.Generator(device="cuda").manual_seed(1)
+kind = sys.argv[5] if len(sys.argv) > 5 else "text"
 q = torch.randn(Q, D, device="cuda", generator=g)
 c = torch.randn(N, D, device="cuda", generator=g)
+if kind == "image":
+    q, c = torch.relu(q), torch.relu(c)
 pc = m.prepare_corpus(c, dtype="bf16", keep_source=False)
 for _ in range(5):
     m.topk(q, pc, k, rescore_exact=False)
