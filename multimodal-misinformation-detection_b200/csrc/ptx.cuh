@@ -111,6 +111,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Device
   }
 }
 
+// ---------------------------------------------------------------- shared-memory accesses by window address
+__device__ __forceinline__ uint64_t ld_shared_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_u64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+// {lo, hi} -> 8 bytes at addr, only where pred holds (no branch)
+__device__ __forceinline__ void st_shared_v2_pred(uint32_t addr, uint32_t lo, uint32_t hi, bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "@p st.shared.v2.b32 [%0], {%1, %2};\n\t"
+      "}" ::"r"(addr),
+      "r"(lo), "r"(hi), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+
 // ---------------------------------------------------------------- elect / misc
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

@@ -96,13 +96,19 @@ __host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta) 
 }
 
 // ---------------------------------------------------------------- warp-cooperative list maintenance
-// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + ((r + slot) & 31)]: conflict-free both
-// when the 32 row-owner lanes append and when the whole warp reads one row.
-__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + ((r + slot) & 31); }
+// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + ((r ^ slot) & 31)]: conflict-free both
+// when the 32 row-owner lanes touch the same slot of their own rows and when the whole warp reads one row.
+__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + ((r ^ slot) & 31); }
+// byte address (shared window) of slot `slot` of the row owned by `lane`
+__device__ __forceinline__ uint32_t key_slot_addr(uint32_t wkeys_addr, int slot, int lane) {
+  return wkeys_addr + static_cast<uint32_t>(slot) * 256u + ((static_cast<uint32_t>(lane ^ slot) & 31u) << 3);
+}
 
-template <int E>
-__device__ __forceinline__ void bitonic_sort_desc(uint64_t (&k)[E], int lane) {
-  // element index i = e * 32 + lane over 32 * E elements; result descending in i.
+// R rows at a time go through the same bitonic network (independent dependency chains: one epilogue warp per
+// scheduler has nobody else to hide the shuffle latency behind).  Element index i = e * 32 + lane over 32 * E
+// elements per row; result descending in i.
+template <int E, int R>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t (&k)[R][E], int lane) {
 #pragma unroll
   for (int size = 2; size <= 32 * E; size <<= 1) {
 #pragma unroll
@@ -112,76 +118,115 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t (&k)[E], int lane) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           if ((e & es) == 0) {
-            const int i_low = e * 32 + lane;
-            const bool desc = (i_low & size) == 0;
-            const uint64_t a = k[e], b = k[e | es];
-            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
-            k[e] = desc ? mx : mn;
-            k[e | es] = desc ? mn : mx;
+            const bool desc = ((e * 32 + lane) & size) == 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const uint64_t a = k[r][e], b = k[r][e | es];
+              const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+              k[r][e] = desc ? mx : mn;
+              k[r][e | es] = desc ? mn : mx;
+            }
           }
         }
       } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          const int i = e * 32 + lane;
-          const uint64_t other = __shfl_xor_sync(kFullMask, k[e], stride);
           const bool lower = (lane & stride) == 0;
-          const bool desc = (i & size) == 0;
+          const bool desc = ((e * 32 + lane) & size) == 0;
           const bool take_max = (lower == desc);
-          const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
-          k[e] = take_max ? mx : mn;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint64_t other = __shfl_xor_sync(kFullMask, k[r][e], stride);
+            const uint64_t mine = k[r][e];
+            const bool mine_gt = mine > other;
+            k[r][e] = (mine_gt == take_max) ? mine : other;
+          }
         }
       }
     }
   }
 }
 
-// Sort the candidate buffers of the rows named in `mask`; keep the best `kprime`.
-//   FINAL = false : write the survivors back, refresh the owner's count.
+struct RowState {
+  int cnt;
+  float thr;
+};
+
+// Sort the candidate buffers of the rows named in `mask` (R of them at a time); keep the best `kprime`.
+//   FINAL = false : write the survivors back.
 //   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
-// In both modes the owner lane's `thr` becomes the row's kprime-th best score once the row holds kprime entries.
-template <int CAP, bool FINAL>
-__device__ __forceinline__ void compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int& cnt, float& thr,
-                                             uint64_t* out_rows, int64_t out_row_stride) {
+// Returns the calling lane's own (count, threshold): a compacted row holds min(n, kprime) entries and, once it
+// holds kprime, its threshold is at least its kprime-th best score.
+template <int CAP, bool FINAL, int R>
+__device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int& cnt,
+                                              float& thr, uint64_t* out_rows, int64_t out_row_stride) {
   constexpr int E = CAP / 32;
-  __syncwarp();
-  while (mask) {
-    const int r = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int n = __shfl_sync(kFullMask, cnt, r);
-    uint64_t k[E];
+  uint64_t k[R][E];
+  int n[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    n[r] = __shfl_sync(kFullMask, cnt, rows[r]);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = e * 32 + lane;
-      k[e] = (i < n) ? wkeys[key_slot_index(i, r)] : 0ull;
+      k[r][e] = (i < n[r]) ? wkeys[key_slot_index(i, rows[r])] : 0ull;
     }
-    bitonic_sort_desc<E>(k, lane);
-    const int keep = n < kprime ? n : kprime;
+  }
+  bitonic_sort_desc<E, R>(k, lane);
+  const int last = kprime - 1;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int keep = n[r] < kprime ? n[r] : kprime;
     if constexpr (!FINAL) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
-        if (i < keep) wkeys[key_slot_index(i, r)] = k[e];
+        if (i < keep) wkeys[key_slot_index(i, rows[r])] = k[r][e];
       }
     } else {
-      uint64_t* out = out_rows + static_cast<int64_t>(r) * out_row_stride;
+      uint64_t* out = out_rows + static_cast<int64_t>(rows[r]) * out_row_stride;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
-        if (i < kprime) out[i] = k[e];   // empty slots are key 0
+        if (i < kprime) out[i] = k[r][e];   // empty slots are key 0
       }
     }
-    const int last = kprime - 1;
-    uint64_t kk = k[0];
+    uint64_t kk = k[r][0];
 #pragma unroll
-    for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[e] : kk;
+    for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[r][e] : kk;
     kk = __shfl_sync(kFullMask, kk, last & 31);
-    if (lane == r) {
+    if (lane == rows[r]) {
       cnt = keep;
-      if (n >= kprime) thr = fmaxf(thr, key_score(kk));   // never below a bound learnt from other CTAs
+      if (n[r] >= kprime) thr = fmaxf(thr, key_score(kk));   // never below a bound learnt from other CTAs
     }
   }
+}
+
+template <int CAP, bool FINAL>
+__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int cnt, float thr,
+                                              uint64_t* out_rows, int64_t out_row_stride) {
+  constexpr int R = CAP == 64 ? 4 : 2;
   __syncwarp();
+  while (__popc(mask) >= R) {
+    int rows[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rows[r] = __ffs(mask) - 1;
+      mask &= mask - 1;
+    }
+    compact_batch<CAP, FINAL, R>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+  }
+  while (mask) {
+    int rows[1];
+    rows[0] = __ffs(mask) - 1;
+    mask &= mask - 1;
+    compact_batch<CAP, FINAL, 1>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+  }
+  __syncwarp();
+  RowState st;
+  st.cnt = cnt;
+  st.thr = thr;
+  return st;
 }
 
 // Per-thread bitonic sort (descending) of a small register array; all indices are compile-time constants.
@@ -344,6 +389,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(warp - 2) * (CAP * 32);
+    const uint32_t wkeys_addr = smem_u32(wkeys);
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
@@ -453,16 +499,19 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
                 if (need) {
                   const float before = thr;
-                  compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                  const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                  cnt = st.cnt;
+                  thr = st.thr;
                   if (thr != before) publish_threshold(p.thr_global, qrow, thr);
                 }
+                // branch-free appends: key = (ordered score << 32) | ~column, stored under a predicate
+                const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float x = v[g * 8 + j];
-                  if (x > thr) {
-                    wkeys[key_slot_index(cnt, lane)] = make_key(x, static_cast<uint32_t>(col0 + g * 8 + j));
-                    ++cnt;
-                  }
+                  const bool take = x > thr;
+                  st_shared_v2_pred(key_slot_addr(wkeys_addr, cnt, lane), ncol - j, float_to_ordered(x), take);
+                  cnt += take ? 1 : 0;
                 }
               }
             }
@@ -476,8 +525,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int64_t row0 = cta_row0 + quarter * 32;
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
         const float before = thr;
-        compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
-                                static_cast<int64_t>(p.n_strips) * p.kprime);
+        const RowState st = compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
+                                                    static_cast<int64_t>(p.n_strips) * p.kprime);
+        cnt = st.cnt;
+        thr = st.thr;
         if (valid && thr != before) publish_threshold(p.thr_global, qrow, thr);
       }
     }
