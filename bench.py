@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional c2 measurement at N=1")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how the per-rank top-K lists are exchanged (peer-memory stores from the re-score kernel, or NCCL all-gather)")
     return ap.parse_args()
 
 
@@ -204,7 +206,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True):
+def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto"):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
     lo, hi = shard_bounds(c_n, world, rank)
@@ -215,7 +217,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps)
+    sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps, exchange=exchange)
     t1.record()
     torch.cuda.synchronize()
     prep_ms = t0.elapsed_time(t1)
@@ -291,7 +293,8 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     flops_per_launch = 2.0 * q_n * (hi - lo) * dim
     return {"q_n": q_n, "c_n": c_n, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
             "ms_per_step": ms_per_step, "prep_ms": prep_ms, "fused_ms": fused_avg, "flops_per_launch": flops_per_launch,
-            "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item())}
+            "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item()),
+            "exchange": sc.exchange if world > 1 else "none (1 GPU)"}
 
 
 def roofline_of(res, peaks, name):
@@ -303,7 +306,7 @@ def roofline_of(res, peaks, name):
     peak = peaks["tflops_sustained"] if long_step else peaks["tflops_burst"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and res["rows_local"] == res["c_n"]:      # the capture is of the unsharded launch
         with open(tpath) as f:
             traffic = json.load(f).get(name)
     return {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -313,6 +316,9 @@ def roofline_of(res, peaks, name):
 
 
 def run_ours(args):
+    # libraries (NCCL, symmetric-memory setup) may print to stdout; the contract is ONE JSON line there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import mmd_retrieval as m
@@ -328,7 +334,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     peaks = measured_peaks()
 
-    res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup)
+    res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange)
     extra = {}
     if world == 1 and not args.no_extra and args.workload != "c2":
         r2 = measure_workload(m, dist, torch, "c2", 1, 0, device, max(args.steps, 20), args.warmup)
@@ -348,7 +354,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "bf16x3 (fp32-accurate split)"}.get(op, op),
             "data": "synthetic",
             "config": {"workload": NAMES[args.workload], "queries": q_n, "corpus_rows": c_n, "dim": dim, "top_k": k,
-                       "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}",
+                       "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}", "exchange": res["exchange"],
                        "l2": "operands exceed L2 (no flush needed)" if res["rows_local"] * dim * 2 > 126e6 else
                              "corpus shard fits L2; queries + source rows re-read per step",
                        "prep_ms": res["prep_ms"], "rescore": "exact fp32 re-score of 18 over-fetched candidates per query",
@@ -361,7 +367,10 @@ def run_ours(args):
         }
         if extra:
             line["also"] = extra
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

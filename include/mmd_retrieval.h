@@ -108,6 +108,11 @@ MMD_API int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtyp
 MMD_API int mmd_topk_merge(const float* scores, const int32_t* idx, int parts, int64_t Q, int k_in, int k_out,
                    float* out_scores, int32_t* out_idx, void* stream);
 
+/* Same merge over packed lists: pairs [parts, Q, k_in] of {int32 score bits (IEEE f32), int32 row} -- the layout
+ * the all-gather of a row-sharded corpus moves (mmd_rescore_pairs writes it).  Lists need not be sorted. */
+MMD_API int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t Q, int k_in, int k_out, float* out_scores,
+                         int32_t* out_idx, void* stream);
+
 /* ---- K5: exact re-score of the selected candidates ------------------------------------------ */
 /* For each query q and candidate j < k_in with cand_idx[q,j] >= 0 :
  *   s = (sum_i q_src[q,i] * c_src[cand_idx[q,j] - idx_offset, i]) * q_inv[q] * c_inv[row]   (fp32)
@@ -116,6 +121,16 @@ MMD_API int mmd_rescore(const void* q_src, int q_dtype, int64_t q_stride, const 
                 int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
                 const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, float* out_scores,
                 int32_t* out_idx, void* stream);
+
+/* Same re-score, but the k_out best are written as packed {score bits, row} pairs to n_dst (1..16) destination
+ * buffers at pair offset dst_offset_pairs + q * k_out + rank.  dst_host is a HOST array of n_dst DEVICE pointers:
+ * one local send buffer for an NCCL all-gather, or every peer's gather buffer ([world][Q][k_out] pairs, offset =
+ * rank * Q * k_out) when the buffers are peer-mapped (NVLink): then the exchange step of the row-sharded path
+ * happens inside this kernel's stores and only a barrier remains.  No reference counterpart (single process). */
+MMD_API int mmd_rescore_pairs(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
+                      int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
+                      const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, void* const* dst_host,
+                      int n_dst, int64_t dst_offset_pairs, void* stream);
 
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* While enabled, every fused contraction launch of mmd_topk_scores is bracketed by CUDA events on its own

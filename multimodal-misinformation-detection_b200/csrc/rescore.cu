@@ -70,12 +70,31 @@ __device__ __forceinline__ float warp_dot(const TQ* __restrict__ a, const TC* __
   return acc;
 }
 
+// Where a re-scored list goes: separate score / index arrays (the plain contract) and/or packed
+// {score bits, global row} pairs written to up to kMaxPairDst buffers -- the local send buffer of the all-gather,
+// or every peer's gather buffer directly (peer-mapped pointers, stores travel over NVLink).
+constexpr int kMaxPairDst = 16;
+struct PairDst {
+  int2* dst[kMaxPairDst];
+  int n;
+  int64_t offset;   // in pairs: rank * Q * k_out for a gather buffer laid out [world][Q][k_out]
+};
+
+__device__ __forceinline__ void emit(float* out_s, int32_t* out_i, const PairDst& pairs, int64_t pos, float sc, int32_t ix) {
+  if (out_s != nullptr) {
+    out_s[pos] = sc;
+    out_i[pos] = ix;
+  }
+  const int2 v = make_int2(__float_as_int(sc), ix);
+  for (int d = 0; d < pairs.n; ++d) pairs.dst[d][pairs.offset + pos] = v;
+}
+
 template <typename TQ, typename TC>
 __global__ void __launch_bounds__(128)
 rescore_kernel(const TQ* __restrict__ q_src, int64_t q_stride, const float* __restrict__ q_inv,
                const TC* __restrict__ c_src, int64_t c_stride, const float* __restrict__ c_inv, int64_t N, int dim,
                const int32_t* __restrict__ cand_idx, int k_in, int64_t idx_offset, int k_out,
-               float* __restrict__ out_s, int32_t* __restrict__ out_i, bool vec_ok) {
+               float* __restrict__ out_s, int32_t* __restrict__ out_i, PairDst pairs, bool vec_ok) {
   __shared__ uint64_t keys[kMaxCand];
   const int64_t q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,31 +120,24 @@ rescore_kernel(const TQ* __restrict__ q_src, int64_t q_stride, const float* __re
       rank += (o > mine) || (o == mine && t < j);
     }
     if (rank < k_out) {
-      if (mine == 0ull) {
-        out_s[q * k_out + rank] = __int_as_float(0xff800000);
-        out_i[q * k_out + rank] = -1;
-      } else {
-        out_s[q * k_out + rank] = key_score(mine);
-        out_i[q * k_out + rank] = static_cast<int32_t>(key_row(mine));
-      }
+      const float sc = mine == 0ull ? __int_as_float(0xff800000) : key_score(mine);
+      const int32_t ix = mine == 0ull ? -1 : static_cast<int32_t>(key_row(mine));
+      emit(out_s, out_i, pairs, q * k_out + rank, sc, ix);
     }
   }
-  for (int i = k_in + threadIdx.x; i < k_out; i += 128) {
-    out_s[q * k_out + i] = __int_as_float(0xff800000);
-    out_i[q * k_out + i] = -1;
-  }
+  for (int i = k_in + threadIdx.x; i < k_out; i += 128) emit(out_s, out_i, pairs, q * k_out + i, __int_as_float(0xff800000), -1);
 }
 
 template <typename TQ, typename TC>
 int launch(const void* q_src, int64_t q_stride, const float* q_inv, const void* c_src, int64_t c_stride,
            const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in, int64_t idx_offset,
-           int k_out, float* out_s, int32_t* out_i, cudaStream_t stream) {
+           int k_out, float* out_s, int32_t* out_i, const PairDst& pairs, cudaStream_t stream) {
   const bool vec_ok = dim % 8 == 0 && reinterpret_cast<uintptr_t>(q_src) % 16 == 0 &&
                       reinterpret_cast<uintptr_t>(c_src) % 16 == 0 && (q_stride * sizeof(TQ)) % 16 == 0 &&
                       (c_stride * sizeof(TC)) % 16 == 0;
   rescore_kernel<TQ, TC><<<static_cast<unsigned>(Q), 128, 0, stream>>>(
       static_cast<const TQ*>(q_src), q_stride, q_inv, static_cast<const TC*>(c_src), c_stride, c_inv, N, dim, cand_idx,
-      k_in, idx_offset, k_out, out_s, out_i, vec_ok);
+      k_in, idx_offset, k_out, out_s, out_i, pairs, vec_ok);
   count_launch();
   MMD_CUDA_OK(cudaGetLastError());
   return MMD_OK;
@@ -134,11 +146,11 @@ int launch(const void* q_src, int64_t q_stride, const float* q_inv, const void* 
 template <typename TQ>
 int dispatch_c(int c_dtype, const void* q_src, int64_t q_stride, const float* q_inv, const void* c_src, int64_t c_stride,
                const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in, int64_t idx_offset,
-               int k_out, float* out_s, int32_t* out_i, cudaStream_t stream) {
+               int k_out, float* out_s, int32_t* out_i, const PairDst& pairs, cudaStream_t stream) {
   switch (c_dtype) {
-    case MMD_SRC_F32: return launch<TQ, float>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
-    case MMD_SRC_F16: return launch<TQ, __half>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
-    case MMD_SRC_BF16: return launch<TQ, __nv_bfloat16>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, stream);
+    case MMD_SRC_F32: return launch<TQ, float>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, pairs, stream);
+    case MMD_SRC_F16: return launch<TQ, __half>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, pairs, stream);
+    case MMD_SRC_BF16: return launch<TQ, __nv_bfloat16>(q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_s, out_i, pairs, stream);
   }
   set_last_error("mmd_rescore: unknown c_dtype %d", c_dtype);
   return MMD_ERR_ARG;
@@ -147,27 +159,61 @@ int dispatch_c(int c_dtype, const void* q_src, int64_t q_stride, const float* q_
 }  // namespace
 }  // namespace mmd
 
-extern "C" int mmd_rescore(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
-                           int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
-                           const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, float* out_scores,
-                           int32_t* out_idx, void* stream) {
-  using namespace mmd;
-  MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k_in > 0 && k_out > 0, "mmd_rescore: Q=%lld N=%lld dim=%d k_in=%d k_out=%d",
+namespace mmd {
+namespace {
+int rescore_any(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src, int c_dtype,
+                int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in,
+                int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, const PairDst& pairs, void* stream,
+                const char* who) {
+  MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k_in > 0 && k_out > 0, "%s: Q=%lld N=%lld dim=%d k_in=%d k_out=%d", who,
               (long long)Q, (long long)N, dim, k_in, k_out);
-  MMD_REQUIRE(k_in <= kMaxCand, "mmd_rescore: k_in %d exceeds %d", k_in, kMaxCand);
+  MMD_REQUIRE(k_in <= kMaxCand, "%s: k_in %d exceeds %d", who, k_in, kMaxCand);
   if (Q == 0) return MMD_OK;
-  MMD_REQUIRE(q_src != nullptr && cand_idx != nullptr && out_scores != nullptr && out_idx != nullptr,
-              "mmd_rescore: null buffer");
-  MMD_REQUIRE(c_src != nullptr || N == 0, "mmd_rescore: null corpus");
-  MMD_REQUIRE(q_stride >= dim && (c_stride >= dim || N == 0), "mmd_rescore: row stride smaller than dim");
+  MMD_REQUIRE(q_src != nullptr && cand_idx != nullptr, "%s: null buffer", who);
+  MMD_REQUIRE((out_scores != nullptr && out_idx != nullptr) || (out_scores == nullptr && out_idx == nullptr && pairs.n > 0),
+              "%s: no output buffer", who);
+  MMD_REQUIRE(c_src != nullptr || N == 0, "%s: null corpus", who);
+  MMD_REQUIRE(q_stride >= dim && (c_stride >= dim || N == 0), "%s: row stride smaller than dim", who);
   int rc = mmd_device_check();
   if (rc != MMD_OK) return rc;
   auto st = static_cast<cudaStream_t>(stream);
   switch (q_dtype) {
-    case MMD_SRC_F32: return dispatch_c<float>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
-    case MMD_SRC_F16: return dispatch_c<__half>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
-    case MMD_SRC_BF16: return dispatch_c<__nv_bfloat16>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, st);
+    case MMD_SRC_F32: return dispatch_c<float>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, pairs, st);
+    case MMD_SRC_F16: return dispatch_c<__half>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, pairs, st);
+    case MMD_SRC_BF16: return dispatch_c<__nv_bfloat16>(c_dtype, q_src, q_stride, q_inv, c_src, c_stride, c_inv, Q, N, dim, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx, pairs, st);
   }
-  set_last_error("mmd_rescore: unknown q_dtype %d", q_dtype);
+  set_last_error("%s: unknown q_dtype %d", who, q_dtype);
   return MMD_ERR_ARG;
+}
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_rescore(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
+                           int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
+                           const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, float* out_scores,
+                           int32_t* out_idx, void* stream) {
+  mmd::PairDst none{};
+  MMD_REQUIRE(out_scores != nullptr && out_idx != nullptr, "mmd_rescore: null output");
+  return mmd::rescore_any(q_src, q_dtype, q_stride, q_inv, c_src, c_dtype, c_stride, c_inv, Q, N, dim, cand_idx, k_in,
+                          idx_offset, k_out, out_scores, out_idx, none, stream, "mmd_rescore");
+}
+
+extern "C" int mmd_rescore_pairs(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src,
+                                 int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
+                                 const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, void* const* dst_host,
+                                 int n_dst, int64_t dst_offset_pairs, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(dst_host != nullptr && n_dst >= 1 && n_dst <= kMaxPairDst, "mmd_rescore_pairs: n_dst=%d (1..%d)", n_dst,
+              kMaxPairDst);
+  MMD_REQUIRE(dst_offset_pairs >= 0, "mmd_rescore_pairs: negative offset");
+  PairDst pairs{};
+  pairs.n = n_dst;
+  pairs.offset = dst_offset_pairs;
+  for (int d = 0; d < n_dst; ++d) {
+    MMD_REQUIRE(dst_host[d] != nullptr && reinterpret_cast<uintptr_t>(dst_host[d]) % 8 == 0,
+                "mmd_rescore_pairs: destination %d is null or not 8-byte aligned", d);
+    pairs.dst[d] = static_cast<int2*>(dst_host[d]);
+  }
+  return rescore_any(q_src, q_dtype, q_stride, q_inv, c_src, c_dtype, c_stride, c_inv, Q, N, dim, cand_idx, k_in,
+                     idx_offset, k_out, nullptr, nullptr, pairs, stream, "mmd_rescore_pairs");
 }

@@ -21,7 +21,8 @@ constexpr uint32_t kFull = 0xffffffffu;
 
 struct MergeSrc {
   const uint64_t* keys;   // [Q][parts * k_in]                    (keys != nullptr)
-  const float* scores;    // [parts][Q][k_in]                      (keys == nullptr)
+  const int2* pairs;      // [parts][Q][k_in] {score bits, row}    (keys == nullptr, pairs != nullptr)
+  const float* scores;    // [parts][Q][k_in]                      (otherwise)
   const int32_t* idx;
   int parts, k_in;
   int64_t Q;
@@ -32,6 +33,10 @@ __device__ __forceinline__ uint64_t load_candidate(const MergeSrc& s, int64_t q,
   if (s.keys != nullptr) return s.keys[q * (static_cast<int64_t>(s.parts) * s.k_in) + i];
   const int part = i / s.k_in, j = i - part * s.k_in;
   const int64_t off = (static_cast<int64_t>(part) * s.Q + q) * s.k_in + j;
+  if (s.pairs != nullptr) {
+    const int2 v = s.pairs[off];
+    return v.y < 0 ? 0ull : make_key(__int_as_float(v.x), static_cast<uint32_t>(v.y));
+  }
   const int32_t r = s.idx[off];
   return r < 0 ? 0ull : make_key(s.scores[off], static_cast<uint32_t>(r));
 }
@@ -225,6 +230,7 @@ int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, 
                        int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream) {
   MergeSrc src{};
   src.keys = partial;
+  src.pairs = nullptr;
   src.scores = nullptr;
   src.idx = nullptr;
   src.parts = partial == nullptr ? 0 : parts;
@@ -254,8 +260,33 @@ extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts
   if (rc != MMD_OK) return rc;
   MergeSrc src{};
   src.keys = nullptr;
+  src.pairs = nullptr;
   src.scores = scores;
   src.idx = idx;
+  src.parts = parts;
+  src.k_in = k_in;
+  src.Q = Q;
+  return launch_merge<false>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t Q, int k_in, int k_out, float* out_scores,
+                                    int32_t* out_idx, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(parts > 0 && Q >= 0 && k_in > 0 && k_out > 0, "mmd_topk_merge_pairs: parts=%d Q=%lld k_in=%d k_out=%d", parts,
+              (long long)Q, k_in, k_out);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(pairs != nullptr && out_scores != nullptr && out_idx != nullptr, "mmd_topk_merge_pairs: null buffer");
+  MMD_REQUIRE(reinterpret_cast<uintptr_t>(pairs) % 8 == 0, "mmd_topk_merge_pairs: pairs must be 8-byte aligned");
+  MMD_REQUIRE((k_in <= 128 && k_out <= 128) || static_cast<int64_t>(parts) * k_in <= 4096,
+              "mmd_topk_merge_pairs: parts*k_in = %lld exceeds 4096 (only lists of <= 128 entries stream)", (long long)parts * k_in);
+  MMD_REQUIRE(k_out <= 4096, "mmd_topk_merge_pairs: k_out %d exceeds 4096", k_out);
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  MergeSrc src{};
+  src.keys = nullptr;
+  src.pairs = static_cast<const int2*>(pairs);
+  src.scores = nullptr;
+  src.idx = nullptr;
   src.parts = parts;
   src.k_in = k_in;
   src.Q = Q;

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional, Tuple, Union
+from typing import Optional, Sequence, Tuple, Union
 
 import torch
 
@@ -172,6 +172,38 @@ def rescore(q: torch.Tensor, q_inv: Optional[torch.Tensor], corpus: PreparedCorp
     return scores, idx
 
 
+def rescore_pairs(q: torch.Tensor, q_inv: Optional[torch.Tensor], corpus: PreparedCorpus, cand_idx: torch.Tensor, k_out: int,
+                  dst_ptrs: Sequence[int], dst_offset_pairs: int = 0) -> None:
+    """K5 with packed output: the k_out best re-scored candidates of every query go, as {score bits, row} int32
+    pairs, to every device pointer in `dst_ptrs` at pair offset dst_offset_pairs + q * k_out (see mmd_rescore_pairs)."""
+    lib = _lib.load()
+    dev = corpus.device
+    n_queries, k_in = cand_idx.shape
+    if n_queries == 0:
+        return
+    src = corpus.source
+    arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    with torch.cuda.device(dev):
+        rc = lib.mmd_rescore_pairs(_ptr(q), _SRC_DTYPE[q.dtype], q.stride(0), _ptr(q_inv), _ptr(src), _SRC_DTYPE[src.dtype],
+                                   src.stride(0) if src.shape[0] else corpus.dim, _ptr(corpus.inv_norm), n_queries, corpus.n,
+                                   corpus.dim, _ptr(cand_idx), k_in, corpus.idx_offset, k_out, arr, len(dst_ptrs),
+                                   int(dst_offset_pairs), _stream_ptr(dev))
+    _lib.check(rc, "mmd_rescore_pairs")
+
+
+def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int] = None):
+    """First half of the default path: K1 on the queries + fused tensor-core top-K' (K' = over-fetched k).
+    Returns (q rows on the device, q inv_norm or None, raw scores f32 [Q,K'], candidate rows i32 [Q,K'])."""
+    q = _as_rows(queries, pc.device)
+    if q.shape[1] != pc.dim:
+        raise RuntimeError(f"query dim {q.shape[1]} does not match corpus dim {pc.dim}")
+    k_eff = min(k, pc.n)
+    kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
+    q_rows, q_inv = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
+    scores, idx = topk_prepared(q_rows, q.shape[0], pc, max(kprime, 1))
+    return q, (q_inv if pc.metric == "cos" else None), scores, idx
+
+
 def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None,
          rescore_exact: Optional[bool] = None, overfetch: Optional[int] = None,
          index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -203,15 +235,12 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
     do_rescore = (pc.source is not None) if rescore_exact is None else bool(rescore_exact)
     if do_rescore and pc.source is None:
         raise ValueError("rescore_exact=True needs a PreparedCorpus built with keep_source=True")
-    kprime = k_eff
     if do_rescore:
-        kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
-    q_rows, q_inv = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
-    scores, idx = topk_prepared(q_rows, n_queries, pc, kprime)
-    if do_rescore:
-        scores, idx = rescore(q, q_inv if pc.metric == "cos" else None, pc, idx, k_eff)
-    elif kprime != k_eff:
-        scores, idx = scores[:, :k_eff].contiguous(), idx[:, :k_eff].contiguous()
+        q, q_inv, _, cand = topk_candidates(q, pc, k_eff, overfetch)
+        scores, idx = rescore(q, q_inv, pc, cand, k_eff)
+    else:
+        q_rows, _ = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
+        scores, idx = topk_prepared(q_rows, n_queries, pc, k_eff)
     if index_dtype != torch.int32:
         idx = idx.to(index_dtype)
     return scores, idx
@@ -248,6 +277,21 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[tor
             rc = _lib.load().mmd_topk_merge(_ptr(scores), _ptr(idx), parts, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
                                             _stream_ptr(scores.device))
         _lib.check(rc, "mmd_topk_merge")
+    return out_s, out_i
+
+
+def merge_pairs(pairs: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4 over packed lists: pairs int32 [parts, Q, k_in, 2] = {score bits, row} -> (scores f32, rows i32) [Q, k_out]."""
+    _require_cuda(pairs.device)
+    parts, n_queries, k_in, two = pairs.shape
+    assert two == 2 and pairs.dtype == torch.int32 and pairs.is_contiguous()
+    out_s = torch.empty((n_queries, k_out), dtype=torch.float32, device=pairs.device)
+    out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=pairs.device)
+    if n_queries:
+        with torch.cuda.device(pairs.device):
+            rc = _lib.load().mmd_topk_merge_pairs(_ptr(pairs), parts, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
+                                                  _stream_ptr(pairs.device))
+        _lib.check(rc, "mmd_topk_merge_pairs")
     return out_s, out_i
 
 

@@ -41,10 +41,19 @@ def _worker(rank, world, port, out):
         cmp = exact.compare_topk(s, i, full, 10, tie_tol=2e-6)
         assert cmp.ok and cmp.max_rel_score_err <= 1e-5, cmp
         assert i[0, :2].tolist() == [5, 30010]
-        # host queries in, the public call moves them
-        s2, i2 = sc.topk(queries, 10)
-        assert torch.equal(i2, i)
-        out[rank] = True
+        # host queries in, the public call moves them; repeated calls reuse the double-buffered exchange
+        for _ in range(3):
+            s2, i2 = sc.topk(queries, 10)
+            assert torch.equal(i2, i) and torch.equal(s2, s)
+        # both exchange implementations give the same bits
+        sc_nccl = m.ShardedCorpus.from_full(corpus.cuda(), exchange="nccl")
+        s3, i3 = sc_nccl.topk(queries.cuda(), 10)
+        assert sc_nccl.exchange == "nccl" and torch.equal(i3, i) and torch.equal(s3, s)
+        # fewer corpus rows than ranks * k: short and empty local lists are padded with (-inf, -1)
+        tiny = m.ShardedCorpus.from_full(corpus[:5].cuda())
+        s4, i4 = tiny.topk(queries.cuda(), 10)
+        assert tuple(i4.shape) == (300, 5) and torch.equal(i4.cpu(), exact.exact_topk(queries, corpus[:5], 5)[1])
+        out[rank] = sc.exchange
     finally:
         dist.destroy_process_group()
 
@@ -56,4 +65,5 @@ def test_sharded_topk_nccl():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
-    assert all(out.get(r) for r in range(world))
+    assert all(out.get(r) in ("peer", "nccl") for r in range(world)), dict(out)
+    print("exchange used:", dict(out))

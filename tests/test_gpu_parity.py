@@ -297,6 +297,34 @@ def test_sharded_equals_unsharded(m):
     assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
 
 
+def test_packed_pairs_exchange_layout(m):
+    """The row-sharded path's exchange format on one GPU: every 'rank' re-scores its shard straight into its slot of a
+    [world, Q, k] gather buffer of {score bits, global row} pairs (two destination buffers at once, as with
+    peer-mapped buffers), then K4 merges the packed lists: identical to the unsharded result."""
+    from mmd_retrieval import ops
+    from mmd_retrieval.sharded import shard_bounds
+    q, c = _data("text", 130, 768, 60), _data("text", 7001, 768, 61)
+    c[7000] = c[2]                                               # equal scores on different shards
+    k, world = 10, 3
+    want_s, want_i = m.topk(q.cuda(), c.cuda(), k)
+    bufs = [torch.zeros((world, q.shape[0], k, 2), dtype=torch.int32, device="cuda") for _ in range(2)]
+    for r in range(world):
+        lo, hi = shard_bounds(c.shape[0], world, r)
+        pc = m.prepare_corpus(c[lo:hi].cuda(), idx_offset=lo)
+        qd, q_inv, _, cand = ops.topk_candidates(q.cuda(), pc, k)
+        ops.rescore_pairs(qd, q_inv, pc, cand, k, [b.data_ptr() for b in bufs], dst_offset_pairs=r * q.shape[0] * k)
+    assert torch.equal(bufs[0], bufs[1])
+    s, i = ops.merge_pairs(bufs[0], k)
+    assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
+    # a shard smaller than k pads its slot with (-inf, -1)
+    pc = m.prepare_corpus(c[:4].cuda())
+    qd, q_inv, _, cand = ops.topk_candidates(q.cuda(), pc, k)
+    one = torch.zeros((1, q.shape[0], k, 2), dtype=torch.int32, device="cuda")
+    ops.rescore_pairs(qd, q_inv, pc, cand, k, [one.data_ptr()])
+    assert bool((one[0, :, 4:, 1] == -1).all()) and bool((one[0, :, :4, 1] >= 0).all())
+    assert bool(torch.isinf(one[0, :, 4:, 0].view(torch.float32)).all())
+
+
 # ------------------------------------------------------------------------------------------ drop-in surfaces
 @pytest.mark.parametrize("name", ["im2im_a.npz", "im2im_b.npz"])
 def test_image_corpus_matches_reference_golden(m, name):
