@@ -251,6 +251,16 @@ __device__ __forceinline__ void thread_sort_desc(float (&v)[N]) {
   }
 }
 
+// Maximum of the 32 scores one tcgen05.ld delivered (3-input maxima on sm_100).
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                 fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+
 // Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
 // value is the next float BELOW a row's current K-th best, so that "score > bound" still admits a score equal
 // to that K-th best (the (score desc, row asc) tie rule is decided later, by the sorts).  Any K-th best of a
@@ -453,37 +463,56 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
         }
+        if constexpr (kDense) {
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
-          tmem_ld_wait();
-          if (c == kTileN / 32 - 1) {
-            // the whole accumulator is in registers: hand the TMEM buffer back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (kCta == 2) mbar_arrive_cluster(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
-            }
-          }
-          const int64_t col0 = col_tile + c * 32;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if constexpr (kDense) {
+          for (int c = 0; c < kTileN / 32; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+            tmem_ld_wait();
+            const int64_t col0 = col_tile + c * 32;
             if (valid) {
               float* out = p.dense + qrow * p.ldd + col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) out[j] = v[j] * p.out_scale;
+                if (col0 + j < p.N) out[j] = __uint_as_float(raw[j]) * p.out_scale;
             }
-          } else {
+          }
+        } else {
+          // ---- pass 1 (filter): branch-free sweep over the 8 chunks of 32 columns with the TMEM loads software
+          // pipelined: which chunks hold a score above some row's threshold?  (Columns beyond N are TMA zero fill;
+          // a false hit on them is sorted out by the edge mask of pass 2.)
+          uint32_t hit = 0u;
+          {
+            uint32_t ra[32], rb[32];
+            const uint32_t t0addr = tmem_base + lane_base + buf * kTileN;
+            tmem_ld_32x32b_x32(t0addr, ra);
+#pragma unroll
+            for (int c = 0; c < kTileN / 32; c += 2) {
+              tmem_ld_wait();
+              tmem_ld_32x32b_x32(t0addr + (c + 1) * 32, rb);
+              hit |= __any_sync(kFullMask, chunk_max(ra) > thr) ? (1u << c) : 0u;
+              tmem_ld_wait();
+              if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(t0addr + (c + 2) * 32, ra);
+              hit |= __any_sync(kFullMask, chunk_max(rb) > thr) ? (2u << c) : 0u;
+            }
+          }
+          // ---- pass 2 (collect): only the chunks that were hit are read again and appended from
+#pragma unroll 1
+          while (hit) {
+            const int c = __ffs(hit) - 1;
+            hit &= hit - 1;
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+            tmem_ld_wait();
+            const int64_t col0 = col_tile + c * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
             if (edge) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j >= p.N) v[j] = kNegInf;
             }
-            // max tree: four group maxima of 8 columns each, then the chunk maximum
             float gm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -491,31 +520,34 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
               gm[g] = fmaxf(a, b);
             }
-            const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-            if (__any_sync(kFullMask, m > thr)) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
-                const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
-                if (need) {
-                  const float before = thr;
-                  const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
-                  cnt = st.cnt;
-                  thr = st.thr;
-                  if (thr != before) publish_threshold(p.thr_global, qrow, thr);
-                }
-                // branch-free appends: key = (ordered score << 32) | ~column, stored under a predicate
-                const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
+            for (int g = 0; g < 4; ++g) {
+              if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
+              const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
+              if (need) {
+                const float before = thr;
+                const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                cnt = st.cnt;
+                thr = st.thr;
+                if (thr != before) publish_threshold(p.thr_global, qrow, thr);
+              }
+              // branch-free appends: key = (ordered score << 32) | ~column, stored under a predicate
+              const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x = v[g * 8 + j];
-                  const bool take = x > thr;
-                  st_shared_v2_pred(key_slot_addr(wkeys_addr, cnt, lane), ncol - j, float_to_ordered(x), take);
-                  cnt += take ? 1 : 0;
-                }
+              for (int j = 0; j < 8; ++j) {
+                const float x = v[g * 8 + j];
+                const bool take = x > thr;
+                st_shared_v2_pred(key_slot_addr(wkeys_addr, cnt, lane), ncol - j, float_to_ordered(x), take);
+                cnt += take ? 1 : 0;
               }
             }
           }
+        }
+        // every score of the tile has been looked at: hand the TMEM buffer back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCta == 2) mbar_arrive_cluster(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
         }
         if (warp == 2 && lane == 0) MMD_TRACE(it, 6);
       }

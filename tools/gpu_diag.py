@@ -145,6 +145,43 @@ def stage_perf():
         print(f"perf Q={Q} N={N} D={D} k={k}: step {ms:.3f} ms ({Q/ms*1e3:.0f} q/s); fused kernel {fm:.3f} ms = {fl/fm/1e9:.0f} TFLOP/s")
 
 
+def stage_perf2():
+    """Other corners: fp8 operands, K = 100, the reference's small-Q calling pattern (HBM-bound), the fp32 configuration."""
+    import torch
+    import mmd_retrieval as m
+    cases = [  # Q, N, D, k, op, rescore
+        (16384, 1000000, 768, 10, "fp8", False), (16384, 1000000, 768, 100, "bf16", False),
+        (16384, 1000000, 768, 100, "fp8", False), (16384, 1000000, 512, 10, "bf16", False),
+        (1, 1000000, 768, 10, "bf16", False), (100, 1000000, 768, 10, "bf16", False), (128, 4000000, 768, 10, "fp8", False),
+        (1000, 10000, 768, 5, "fp32", False), (1000, 10000, 768, 5, "bf16", True)]
+    for (Q, N, D, k, op, resc) in cases:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        q = torch.randn(Q, D, device="cuda", generator=g)
+        c = torch.randn(N, D, device="cuda", generator=g)
+        pc = m.prepare_corpus(c, dtype=op, keep_source=resc)
+        del c
+        for _ in range(2):
+            m.topk(q, pc, k, rescore_exact=resc)
+        torch.cuda.synchronize()
+        m.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            m.topk(q, pc, k, rescore_exact=resc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        fused = m.profile_collect()
+        m.profile_enable(False)
+        fm = sum(fused) / len(fused)
+        fl = 2.0 * Q * N * D
+        gb = pc.rows.numel() / fm / 1e6
+        print(f"perf2 Q={Q} N={N} D={D} k={k} op={op}: step {ms:.3f} ms ({Q/ms*1e3:.0f} q/s); fused {fm:.3f} ms = {fl/fm/1e9:.0f} TFLOP/s, "
+              f"corpus stream {gb:.0f} GB/s")
+        del pc
+
+
 def stage_k1perf():
     import torch
     import mmd_retrieval as m
@@ -169,7 +206,7 @@ def stage_k1perf():
         del x, out
 
 
-STAGES = {"k1perf": stage_k1perf, "k1": stage_k1, "dense1": stage_dense1, "dense2": stage_dense2, "topk": stage_topk, "perf": stage_perf}
+STAGES = {"k1perf": stage_k1perf, "k1": stage_k1, "dense1": stage_dense1, "dense2": stage_dense2, "topk": stage_topk, "perf": stage_perf, "perf2": stage_perf2}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--run":
