@@ -84,6 +84,16 @@ MMD_API int mmd_normalize_cast(const void* src, int src_dtype, int64_t rows, int
                        int normalize, float eps, int op_dtype, int side, void* dst, float* inv_norm,
                        void* stream);
 
+/* One SEGMENT of a joint (multi-modality) prepared row: like mmd_normalize_cast, but every value is also multiplied by
+ * `scale` and the rows are written with pitch dst_row_bytes starting at `dst` (= row 0 of the joint buffer + the
+ * segment's byte offset, a multiple of 16).  Laying the modalities of a claim / an evidence side by side along K, with
+ * the query side scaled by the modality weight w_m, makes ONE contraction compute sum_m w_m * cos(q_m, c_m) -- the joint
+ * image+text score (BASELINE.json configs[3]; the reference's closest counterpart is the concat + sort of the two
+ * hit lists, src/evidence/text2text_retrieval.py:97-118).  Not available for MMD_OP_BF16X3. */
+MMD_API int mmd_normalize_cast_segment(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride,
+                               int normalize, float eps, float scale, int op_dtype, int side, void* dst,
+                               int64_t dst_row_bytes, float* inv_norm, void* stream);
+
 /* ---- K2+K3: tensor-core score contraction with fused top-K ---------------------------------- */
 /* Largest K the fused selection supports. */
 MMD_API int mmd_topk_max_k(void);
@@ -131,6 +141,15 @@ MMD_API int mmd_rescore_pairs(const void* q_src, int q_dtype, int64_t q_stride, 
                       int c_dtype, int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim,
                       const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out, void* const* dst_host,
                       int n_dst, int64_t dst_offset_pairs, void* stream);
+
+/* Joint re-score over n_seg (1..4) modalities: s = sum_m weight[m] * <q_m, c_m> * q_inv[m][q] * c_inv[m][row] in fp32.
+ * Every *_host argument is a HOST array of n_seg entries (device pointers / dtypes / strides / dims / weights);
+ * q_inv_host / c_inv_host (or single entries) may be NULL (= 1). */
+MMD_API int mmd_rescore_joint(int n_seg, const void* const* q_src_host, const int* q_dtype_host, const int64_t* q_stride_host,
+                      const float* const* q_inv_host, const void* const* c_src_host, const int* c_dtype_host,
+                      const int64_t* c_stride_host, const float* const* c_inv_host, const int* dim_host,
+                      const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
+                      int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, void* stream);
 
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* While enabled, every fused contraction launch of mmd_topk_scores is bracketed by CUDA events on its own

@@ -126,7 +126,7 @@ __device__ __forceinline__ void store8(uint8_t* __restrict__ dst_row, int g, int
 template <typename T, int OP, bool kVec, int G, bool kTail>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t src_stride, int normalize,
-                      float eps, int side, uint8_t* __restrict__ dst, int64_t dpad, int64_t row_bytes,
+                      float eps, float scale, int side, uint8_t* __restrict__ dst, int64_t dpad, int64_t row_bytes,
                       float* __restrict__ inv_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -175,7 +175,7 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
       if (g < n_groups) {
         float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = normalize ? cache[i][j] / denom : cache[i][j];
+        for (int j = 0; j < 8; ++j) y[j] = (normalize ? cache[i][j] / denom : cache[i][j]) * scale;
         store8<OP>(drow, g, dpad, side, y);
       }
     }
@@ -184,7 +184,7 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
         float v[8];
         load8<T, kVec>(row, g, dim, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = normalize ? v[j] / denom : v[j];
+        for (int j = 0; j < 8; ++j) v[j] = (normalize ? v[j] / denom : v[j]) * scale;
         store8<OP>(drow, g, dpad, side, v);
       }
     }
@@ -193,25 +193,25 @@ normalize_cast_kernel(const T* __restrict__ src, int64_t rows, int dim, int64_t 
 
 template <typename T, int OP, bool kVec, int G, bool kTail>
 void launch_g(unsigned grid, cudaStream_t stream, const T* s, int64_t rows, int dim, int64_t src_stride, int normalize,
-              float eps, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
+              float eps, float scale, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
   normalize_cast_kernel<T, OP, kVec, G, kTail><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-      s, rows, dim, src_stride, normalize, eps, side, d, lay.dpad, lay.row_bytes, inv_norm);
+      s, rows, dim, src_stride, normalize, eps, scale, side, d, lay.dpad, lay.row_bytes, inv_norm);
 }
 
 template <typename T, int OP, bool kVec>
 void launch_v(unsigned grid, cudaStream_t stream, const T* s, int64_t rows, int dim, int64_t src_stride, int normalize,
-              float eps, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
+              float eps, float scale, int side, uint8_t* d, const PreparedLayout& lay, float* inv_norm) {
   const int per_lane = static_cast<int>(ceil_div(lay.dpad / 8, 32));
-  if (per_lane <= 1) launch_g<T, OP, kVec, 1, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else if (per_lane <= 2) launch_g<T, OP, kVec, 2, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else if (per_lane <= 3) launch_g<T, OP, kVec, 3, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else if (per_lane <= 4) launch_g<T, OP, kVec, 4, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else if (per_lane <= kMaxCachedGroups) launch_g<T, OP, kVec, kMaxCachedGroups, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else launch_g<T, OP, kVec, kMaxCachedGroups, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  if (per_lane <= 1) launch_g<T, OP, kVec, 1, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else if (per_lane <= 2) launch_g<T, OP, kVec, 2, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else if (per_lane <= 3) launch_g<T, OP, kVec, 3, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else if (per_lane <= 4) launch_g<T, OP, kVec, 4, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else if (per_lane <= kMaxCachedGroups) launch_g<T, OP, kVec, kMaxCachedGroups, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else launch_g<T, OP, kVec, kMaxCachedGroups, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
 }
 
 template <typename T, int OP>
-int launch(const void* src, int64_t rows, int dim, int64_t src_stride, int normalize, float eps, int side, void* dst,
+int launch(const void* src, int64_t rows, int dim, int64_t src_stride, int normalize, float eps, float scale, int side, void* dst,
            const PreparedLayout& lay, float* inv_norm, cudaStream_t stream) {
   const bool vec = (reinterpret_cast<uintptr_t>(src) % 16 == 0) && ((src_stride * sizeof(T)) % 16 == 0);
   int dev = 0, sms = 148;
@@ -222,21 +222,21 @@ int launch(const void* src, int64_t rows, int dim, int64_t src_stride, int norma
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   auto* s = static_cast<const T*>(src);
   auto* d = static_cast<uint8_t*>(dst);
-  if (vec) launch_v<T, OP, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
-  else launch_v<T, OP, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, side, d, lay, inv_norm);
+  if (vec) launch_v<T, OP, true>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
+  else launch_v<T, OP, false>(grid, stream, s, rows, dim, src_stride, normalize, eps, scale, side, d, lay, inv_norm);
   count_launch();
   MMD_CUDA_OK(cudaGetLastError());
   return MMD_OK;
 }
 
 template <typename T>
-int dispatch_op(int op, const void* src, int64_t rows, int dim, int64_t src_stride, int normalize, float eps, int side,
+int dispatch_op(int op, const void* src, int64_t rows, int dim, int64_t src_stride, int normalize, float eps, float scale, int side,
                 void* dst, const PreparedLayout& lay, float* inv_norm, cudaStream_t stream) {
   switch (op) {
-    case MMD_OP_BF16: return launch<T, MMD_OP_BF16>(src, rows, dim, src_stride, normalize, eps, side, dst, lay, inv_norm, stream);
-    case MMD_OP_F16: return launch<T, MMD_OP_F16>(src, rows, dim, src_stride, normalize, eps, side, dst, lay, inv_norm, stream);
-    case MMD_OP_E4M3: return launch<T, MMD_OP_E4M3>(src, rows, dim, src_stride, normalize, eps, side, dst, lay, inv_norm, stream);
-    case MMD_OP_BF16X3: return launch<T, MMD_OP_BF16X3>(src, rows, dim, src_stride, normalize, eps, side, dst, lay, inv_norm, stream);
+    case MMD_OP_BF16: return launch<T, MMD_OP_BF16>(src, rows, dim, src_stride, normalize, eps, scale, side, dst, lay, inv_norm, stream);
+    case MMD_OP_F16: return launch<T, MMD_OP_F16>(src, rows, dim, src_stride, normalize, eps, scale, side, dst, lay, inv_norm, stream);
+    case MMD_OP_E4M3: return launch<T, MMD_OP_E4M3>(src, rows, dim, src_stride, normalize, eps, scale, side, dst, lay, inv_norm, stream);
+    case MMD_OP_BF16X3: return launch<T, MMD_OP_BF16X3>(src, rows, dim, src_stride, normalize, eps, scale, side, dst, lay, inv_norm, stream);
   }
   set_last_error("mmd_normalize_cast: unknown op_dtype %d", op);
   return MMD_ERR_ARG;
@@ -253,26 +253,50 @@ extern "C" int mmd_prepared_layout(int op_dtype, int dim, int64_t* kdim, int64_t
   return MMD_OK;
 }
 
-extern "C" int mmd_normalize_cast(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride,
-                                  int normalize, float eps, int op_dtype, int side, void* dst, float* inv_norm,
-                                  void* stream) {
-  using namespace mmd;
-  MMD_REQUIRE(rows >= 0 && dim > 0, "mmd_normalize_cast: rows=%lld dim=%d", (long long)rows, dim);
+namespace mmd {
+namespace {
+int normalize_cast_any(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride, int normalize,
+                       float eps, float scale, int op_dtype, int side, void* dst, int64_t dst_row_bytes, float* inv_norm,
+                       void* stream, const char* who) {
+  MMD_REQUIRE(rows >= 0 && dim > 0, "%s: rows=%lld dim=%d", who, (long long)rows, dim);
   if (rows == 0) return MMD_OK;
-  MMD_REQUIRE(src != nullptr && dst != nullptr, "mmd_normalize_cast: null buffer");
-  MMD_REQUIRE(src_row_stride >= dim, "mmd_normalize_cast: src_row_stride %lld < dim %d", (long long)src_row_stride, dim);
-  MMD_REQUIRE(side == MMD_SIDE_QUERY || side == MMD_SIDE_CORPUS, "mmd_normalize_cast: bad side %d", side);
-  MMD_REQUIRE(reinterpret_cast<uintptr_t>(dst) % 16 == 0, "mmd_normalize_cast: dst must be 16-byte aligned");
+  MMD_REQUIRE(src != nullptr && dst != nullptr, "%s: null buffer", who);
+  MMD_REQUIRE(src_row_stride >= dim, "%s: src_row_stride %lld < dim %d", who, (long long)src_row_stride, dim);
+  MMD_REQUIRE(side == MMD_SIDE_QUERY || side == MMD_SIDE_CORPUS, "%s: bad side %d", who, side);
+  MMD_REQUIRE(reinterpret_cast<uintptr_t>(dst) % 16 == 0, "%s: dst must be 16-byte aligned", who);
   PreparedLayout lay;
-  MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "mmd_normalize_cast: bad op_dtype %d", op_dtype);
+  MMD_REQUIRE(prepared_layout(op_dtype, dim, &lay), "%s: bad op_dtype %d", who, op_dtype);
+  if (dst_row_bytes != 0) {
+    MMD_REQUIRE(op_dtype != MMD_OP_BF16X3, "%s: the 3-limb fp32 configuration cannot be laid out as a segment", who);
+    MMD_REQUIRE(dst_row_bytes >= lay.row_bytes && dst_row_bytes % 16 == 0, "%s: dst_row_bytes %lld (segment needs %lld, 16-byte multiple)",
+                who, (long long)dst_row_bytes, (long long)lay.row_bytes);
+    lay.row_bytes = dst_row_bytes;
+  }
   int rc = mmd_device_check();
   if (rc != MMD_OK) return rc;
   auto st = static_cast<cudaStream_t>(stream);
   switch (src_dtype) {
-    case MMD_SRC_F32: return dispatch_op<float>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, side, dst, lay, inv_norm, st);
-    case MMD_SRC_F16: return dispatch_op<__half>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, side, dst, lay, inv_norm, st);
-    case MMD_SRC_BF16: return dispatch_op<__nv_bfloat16>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, side, dst, lay, inv_norm, st);
+    case MMD_SRC_F32: return dispatch_op<float>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, scale, side, dst, lay, inv_norm, st);
+    case MMD_SRC_F16: return dispatch_op<__half>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, scale, side, dst, lay, inv_norm, st);
+    case MMD_SRC_BF16: return dispatch_op<__nv_bfloat16>(op_dtype, src, rows, dim, src_row_stride, normalize, eps, scale, side, dst, lay, inv_norm, st);
   }
-  set_last_error("mmd_normalize_cast: unknown src_dtype %d", src_dtype);
+  set_last_error("%s: unknown src_dtype %d", who, src_dtype);
   return MMD_ERR_ARG;
+}
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_normalize_cast(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride,
+                                  int normalize, float eps, int op_dtype, int side, void* dst, float* inv_norm,
+                                  void* stream) {
+  return mmd::normalize_cast_any(src, src_dtype, rows, dim, src_row_stride, normalize, eps, 1.0f, op_dtype, side, dst, 0,
+                                 inv_norm, stream, "mmd_normalize_cast");
+}
+
+extern "C" int mmd_normalize_cast_segment(const void* src, int src_dtype, int64_t rows, int dim, int64_t src_row_stride,
+                                          int normalize, float eps, float scale, int op_dtype, int side, void* dst,
+                                          int64_t dst_row_bytes, float* inv_norm, void* stream) {
+  MMD_REQUIRE(dst_row_bytes > 0, "mmd_normalize_cast_segment: dst_row_bytes must be positive");
+  return mmd::normalize_cast_any(src, src_dtype, rows, dim, src_row_stride, normalize, eps, scale, op_dtype, side, dst,
+                                 dst_row_bytes, inv_norm, stream, "mmd_normalize_cast_segment");
 }

@@ -161,6 +161,114 @@ int dispatch_c(int c_dtype, const void* q_src, int64_t q_stride, const float* q_
 
 namespace mmd {
 namespace {
+
+// ---------------------------------------------------------------- joint (multi-modality) re-score
+// score(q, c) = sum_m weight_m * <q_m, c_m> * q_inv_m[q] * c_inv_m[c]  over up to kMaxSeg modalities, each with its own
+// embeddings (own dim / dtype / stride).  Element types are switched at run time (uniform per segment).
+constexpr int kMaxSeg = 4;
+struct Segments {
+  const void* q_src[kMaxSeg];
+  const void* c_src[kMaxSeg];
+  const float* q_inv[kMaxSeg];
+  const float* c_inv[kMaxSeg];
+  int64_t q_stride[kMaxSeg], c_stride[kMaxSeg];
+  int dim[kMaxSeg], q_dtype[kMaxSeg], c_dtype[kMaxSeg];
+  float weight[kMaxSeg];
+  int n;
+};
+
+__device__ __forceinline__ float load_rt(const void* base, int dtype, int64_t i) {
+  if (dtype == MMD_SRC_F32) return static_cast<const float*>(base)[i];
+  if (dtype == MMD_SRC_F16) return __half2float(static_cast<const __half*>(base)[i]);
+  return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
+}
+
+__global__ void __launch_bounds__(128)
+rescore_multi_kernel(Segments sg, int64_t N, const int32_t* __restrict__ cand_idx, int k_in, int64_t idx_offset, int k_out,
+                     float* __restrict__ out_s, int32_t* __restrict__ out_i) {
+  __shared__ uint64_t keys[kMaxCand];
+  const int64_t q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < k_in; j += 4) {
+    const int32_t gi = cand_idx[q * k_in + j];
+    uint64_t key = 0ull;
+    const int64_t row = static_cast<int64_t>(gi) - idx_offset;
+    if (gi >= 0 && row >= 0 && row < N) {
+      float total = 0.0f;
+      for (int m = 0; m < sg.n; ++m) {
+        float acc = 0.0f;
+        const int64_t qo = q * sg.q_stride[m], co = row * sg.c_stride[m];
+        for (int i = lane; i < sg.dim[m]; i += 32)
+          acc = fmaf(load_rt(sg.q_src[m], sg.q_dtype[m], qo + i), load_rt(sg.c_src[m], sg.c_dtype[m], co + i), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float qi = sg.q_inv[m] != nullptr ? sg.q_inv[m][q] : 1.0f;
+        const float ci = sg.c_inv[m] != nullptr ? sg.c_inv[m][row] : 1.0f;
+        total = fmaf(sg.weight[m], acc * qi * ci, total);
+      }
+      key = make_key(total, static_cast<uint32_t>(gi));
+    }
+    if (lane == 0) keys[j] = key;
+  }
+  __syncthreads();
+  PairDst none{};
+  for (int j = threadIdx.x; j < k_in; j += 128) {
+    const uint64_t mine = keys[j];
+    int rank = 0;
+    for (int t = 0; t < k_in; ++t) {
+      const uint64_t o = keys[t];
+      rank += (o > mine) || (o == mine && t < j);
+    }
+    if (rank < k_out) {
+      const float sc = mine == 0ull ? __int_as_float(0xff800000) : key_score(mine);
+      const int32_t ix = mine == 0ull ? -1 : static_cast<int32_t>(key_row(mine));
+      emit(out_s, out_i, none, q * k_out + rank, sc, ix);
+    }
+  }
+  for (int i = k_in + threadIdx.x; i < k_out; i += 128) emit(out_s, out_i, none, q * k_out + i, __int_as_float(0xff800000), -1);
+}
+
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_rescore_joint(int n_seg, const void* const* q_src_host, const int* q_dtype_host, const int64_t* q_stride_host,
+                                 const float* const* q_inv_host, const void* const* c_src_host, const int* c_dtype_host,
+                                 const int64_t* c_stride_host, const float* const* c_inv_host, const int* dim_host,
+                                 const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
+                                 int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, "mmd_rescore_joint: n_seg=%d (1..%d)", n_seg, kMaxSeg);
+  MMD_REQUIRE(Q >= 0 && N >= 0 && k_in > 0 && k_out > 0 && k_in <= kMaxCand, "mmd_rescore_joint: Q=%lld N=%lld k_in=%d k_out=%d",
+              (long long)Q, (long long)N, k_in, k_out);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(cand_idx != nullptr && out_scores != nullptr && out_idx != nullptr, "mmd_rescore_joint: null buffer");
+  Segments sg{};
+  sg.n = n_seg;
+  for (int m = 0; m < n_seg; ++m) {
+    MMD_REQUIRE(q_src_host[m] != nullptr && (c_src_host[m] != nullptr || N == 0) && dim_host[m] > 0,
+                "mmd_rescore_joint: segment %d has a null buffer or non-positive dim", m);
+    MMD_REQUIRE(q_dtype_host[m] >= 0 && q_dtype_host[m] <= 2 && c_dtype_host[m] >= 0 && c_dtype_host[m] <= 2,
+                "mmd_rescore_joint: segment %d has an unknown dtype", m);
+    MMD_REQUIRE(q_stride_host[m] >= dim_host[m] && (c_stride_host[m] >= dim_host[m] || N == 0),
+                "mmd_rescore_joint: segment %d row stride smaller than dim", m);
+    sg.q_src[m] = q_src_host[m]; sg.c_src[m] = c_src_host[m];
+    sg.q_inv[m] = q_inv_host != nullptr ? q_inv_host[m] : nullptr;
+    sg.c_inv[m] = c_inv_host != nullptr ? c_inv_host[m] : nullptr;
+    sg.q_stride[m] = q_stride_host[m]; sg.c_stride[m] = c_stride_host[m];
+    sg.dim[m] = dim_host[m]; sg.q_dtype[m] = q_dtype_host[m]; sg.c_dtype[m] = c_dtype_host[m];
+    sg.weight[m] = weight_host[m];
+  }
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  rescore_multi_kernel<<<static_cast<unsigned>(Q), 128, 0, static_cast<cudaStream_t>(stream)>>>(sg, N, cand_idx, k_in, idx_offset,
+                                                                                                 k_out, out_scores, out_idx);
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
+}
+
+namespace mmd {
+namespace {
 int rescore_any(const void* q_src, int q_dtype, int64_t q_stride, const float* q_inv, const void* c_src, int c_dtype,
                 int64_t c_stride, const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in,
                 int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, const PairDst& pairs, void* stream,

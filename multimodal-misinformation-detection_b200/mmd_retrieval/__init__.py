@@ -9,6 +9,7 @@ Public surface (mirrors the reference's entry points; see DESIGN.md / INTEGRATIO
     cos_sim / dot_score                            drop-in score functions
     ImageCorpus / ImageSimilarity                  drop-in for src/evidence/im2im_retrieval.py
     ShardedCorpus                                  row-sharded corpus over the GPUs of one box
+    prepare_joint / topk_joint                     joint image+text retrieval, weighted score fusion in one contraction
 
 All arithmetic runs in libmmd.so (hand-written sm_100a CUDA behind a C ABI).  There is no CPU fallback.
 """
@@ -19,10 +20,11 @@ from .postfilter import dedupe_by_score, hits_at_k
 from .semantic_search import semantic_search, cos_sim, dot_score, clear_cache
 from .image_corpus import ImageCorpus, ImageSimilarity, calculate_topk_accuracy_image_retrieval
 from .sharded import ShardedCorpus, shard_bounds
+from .joint import JointCorpus, prepare_joint, topk_joint
 
 __all__ = [
     "MmdError", "LIB_PATH", "PreparedCorpus", "prepare_corpus", "topk", "dense_scores", "merge_topk", "normalize_cast",
     "max_k", "profile_enable", "profile_collect", "launch_count", "dedupe_by_score", "hits_at_k", "semantic_search",
     "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "calculate_topk_accuracy_image_retrieval",
-    "ShardedCorpus", "shard_bounds",
+    "ShardedCorpus", "shard_bounds", "JointCorpus", "prepare_joint", "topk_joint",
 ]

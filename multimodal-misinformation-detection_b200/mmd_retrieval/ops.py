@@ -131,8 +131,10 @@ def max_k() -> int:
 
 
 def overfetch_for(k: int, n: int) -> int:
-    """Candidates kept by the low-precision pass when an exact re-score follows."""
-    return max(1, min(n, k + max(8, k // 2), max_k()))
+    """Candidates kept by the low-precision pass when an exact re-score follows: k + max(8, k/2), but never so
+    many that the per-row candidate buffer of the fused kernel (128 entries for lists longer than 32) is left
+    with fewer than 24 free slots between two compactions."""
+    return max(1, min(n, max(k, min(k + max(8, k // 2), 104)), max_k()))
 
 
 def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -325,6 +325,49 @@ def test_packed_pairs_exchange_layout(m):
     assert bool(torch.isinf(one[0, :, 4:, 0].view(torch.float32)).all())
 
 
+# ------------------------------------------------------------------------------------------ joint image+text fusion
+@pytest.mark.parametrize("op,dims,weights", [("bf16", (512, 512), (0.5, 0.5)), ("bf16", (768, 2048), (0.7, 0.3)),
+                                             ("fp16", (100, 36), (0.25, 0.75)), ("bf16", (64, 64, 32), (0.2, 0.3, 0.5))])
+def test_joint_fusion_matches_oracle(m, op, dims, weights):
+    """sum_m w_m * cos(q_m, c_m) from ONE contraction over side-by-side segments + exact joint re-score, against the
+    float64 fusion oracle (BASELINE configs[3] at a size the oracle finishes in seconds)."""
+    from oracle import fusion
+    n_q, n_c, k = 150, 4000, 10
+    qs = [_data("image" if d == 2048 else "text", n_q, d, 70 + j) for j, d in enumerate(dims)]
+    cs = [_data("image" if d == 2048 else "text", n_c, d, 80 + j) for j, d in enumerate(dims)]
+    jc = m.prepare_joint([c.cuda() for c in cs], weights, dtype=op)
+    full = fusion.fused_scores(qs, cs, weights)
+    s, i = m.topk_joint([q.cuda() for q in qs], jc, k)
+    cmp = exact.compare_topk(s, i, full, k, tie_tol=2e-6)
+    assert cmp.ok and cmp.max_rel_score_err <= FP32_RTOL, cmp
+    # raw tensor-core scores (no re-score): within the operand rounding of the weighted sum
+    s_raw, i_raw = m.topk_joint([q.cuda() for q in qs], jc, k, rescore_exact=False)
+    picked = torch.gather(full, 1, i_raw.cpu())
+    assert float((s_raw.cpu().double() - picked).abs().max()) <= (2e-3 if op == "bf16" else 3e-4)
+    # weight (1, 0, ...) degenerates to single-modality retrieval on modality 0
+    one = [1.0] + [0.0] * (len(dims) - 1)
+    s1, i1 = m.topk_joint([q.cuda() for q in qs], m.prepare_joint([c.cuda() for c in cs], one, dtype=op), k)
+    s0, i0 = m.topk(qs[0].cuda(), m.prepare_corpus(cs[0].cuda(), dtype=op), k)
+    assert torch.equal(i1, i0) and float((s1 - s0).abs().max()) <= 1e-6
+
+
+def test_joint_fusion_fp8_and_errors(m):
+    from oracle import fusion
+    qs = [_data("text", 64, 512, 90), _data("text", 64, 512, 91)]
+    cs = [_data("text", 3000, 512, 92), _data("text", 3000, 512, 93)]
+    jc = m.prepare_joint([c.cuda() for c in cs], dtype="fp8")
+    s, i = m.topk_joint([q.cuda() for q in qs], jc, 10, overfetch=60)
+    want_s, want_i = fusion.fused_topk(qs, cs, (0.5, 0.5), 10)
+    recall = sum(len(set(a) & set(b)) for a, b in zip(i.cpu().tolist(), want_i.tolist())) / want_i.numel()
+    assert recall >= 0.97
+    with pytest.raises(ValueError):
+        m.prepare_joint([cs[0].cuda(), cs[1][:10].cuda()])
+    with pytest.raises(ValueError):
+        m.prepare_joint([c.cuda() for c in cs], dtype="fp32")
+    with pytest.raises(RuntimeError):
+        m.topk_joint([qs[0].cuda(), qs[1][:, :100].cuda()], jc, 5)
+
+
 # ------------------------------------------------------------------------------------------ drop-in surfaces
 @pytest.mark.parametrize("name", ["im2im_a.npz", "im2im_b.npz"])
 def test_image_corpus_matches_reference_golden(m, name):

@@ -126,3 +126,20 @@ def test_image_eval_planted_positive():
     keys = [f"k{i}" for i in range(200)]
     acc = evalmetrics.image_eval(exact.exact_scores(q, c, eps=1e-6), keys, [f"k{i}" for i in range(10)])
     assert acc[1] == 1.0 and acc[10] == 1.0
+
+
+def test_fusion_oracle_consistency():
+    """oracle/fusion.py: weights (1, 0) reduce to the single-modality oracle; the fused matrix is linear in the weights;
+    concat_and_sort restates the reference's two-list merge (text2text_retrieval.py:97-118)."""
+    from oracle import exact, fusion
+    gen = torch.Generator().manual_seed(5)
+    qs = [torch.randn(7, 16, generator=gen), torch.randn(7, 24, generator=gen)]
+    cs = [torch.randn(50, 16, generator=gen), torch.randn(50, 24, generator=gen)]
+    a = fusion.fused_scores(qs, cs, (1.0, 0.0))
+    assert torch.allclose(a, exact.exact_scores(qs[0], cs[0]))
+    mix = fusion.fused_scores(qs, cs, (0.3, 0.7))
+    assert torch.allclose(mix, 0.3 * exact.exact_scores(qs[0], cs[0]) + 0.7 * exact.exact_scores(qs[1], cs[1]))
+    s, i = fusion.fused_topk(qs, cs, (0.5, 0.5), 5)
+    assert bool((s[:, :-1] >= s[:, 1:]).all()) and tuple(i.shape) == (7, 5)
+    merged = fusion.concat_and_sort([("train_1", 0.9), ("train_2", 0.5)], [("test_3", 0.9), ("test_4", 0.7)], 3)
+    assert merged == [("train_1", 0.9), ("test_4", 0.7), ("train_2", 0.5)]
