@@ -47,7 +47,10 @@ def _as_rows(x, device: Optional[torch.device] = None) -> torch.Tensor:
     """list / ndarray / tensor -> 2-D tensor with unit inner stride on `device` (fp32/fp16/bf16)."""
     if not isinstance(x, torch.Tensor):
         import numpy as np
-        x = torch.as_tensor(np.asarray(x))
+        arr = np.asarray(x)
+        if not arr.flags.writeable:          # e.g. a read-only memory map: torch needs a writable buffer
+            arr = arr.copy()
+        x = torch.as_tensor(arr)
     if x.dim() == 1:
         x = x.unsqueeze(0)
     if x.dim() != 2:

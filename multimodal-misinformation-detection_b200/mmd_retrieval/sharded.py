@@ -73,7 +73,8 @@ class ShardedCorpus:
 
     def __init__(self, local_rows, n_total: int, start: int, group=None, dtype: str = "bf16", metric: str = "cos",
                  eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto",
-                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, prepare: Optional[Callable] = None):
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, prepare: Optional[Callable] = None,
+                 _shard=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -88,14 +89,17 @@ class ShardedCorpus:
         self._injected = local_topk is not None or merge is not None or prepare is not None
         self._local_topk = local_topk or _cuda_local_topk
         self._merge = merge or _cuda_merge
-        if prepare is None:
+        if _shard is not None:
+            self.shard = _shard
+            self.n_local = _shard.n
+        elif prepare is None:
             from . import ops
             self.shard = ops.prepare_corpus(local_rows, dtype=dtype, metric=metric, eps=eps, keep_source=keep_source,
                                             idx_offset=self.start)
             self.n_local = self.shard.n
         else:
             self.shard = prepare(local_rows, self.start)
-            self.n_local = int(local_rows.shape[0])
+            self.n_local = int(local_rows.shape[0]) if hasattr(local_rows, "shape") else int(local_rows[0].shape[0])
 
     @classmethod
     def from_full(cls, corpus: torch.Tensor, group=None, **kw) -> "ShardedCorpus":
@@ -104,6 +108,29 @@ class ShardedCorpus:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi = shard_bounds(corpus.shape[0], world, rank)
         return cls(corpus[lo:hi], corpus.shape[0], lo, group=group, **kw)
+
+    @classmethod
+    def from_prepared(cls, shard, n_total: int, group=None, exchange: str = "auto") -> "ShardedCorpus":
+        """Wrap this rank's already prepared shard (e.g. corpus_io.prepare_streamed(..., idx_offset=start))."""
+        return cls(None, n_total, shard.idx_offset, group=group, exchange=exchange, _shard=shard)
+
+    @classmethod
+    def from_joint(cls, local_corpora, n_total: int, start: int, weights=None, group=None, dtype: str = "bf16",
+                   metric: str = "cos", eps: float = 1e-12) -> "ShardedCorpus":
+        """Row-sharded JOINT (multi-modality) corpus: local_corpora = this rank's rows of every modality; queries are
+        passed to topk() as a list with one matrix per modality."""
+        from . import joint, ops
+
+        def prepare(rows, first):
+            return joint.prepare_joint(rows, weights, dtype=dtype, metric=metric, eps=eps, idx_offset=first)
+
+        def local_topk(queries, shard, k):
+            return joint.topk_joint(queries, shard, k, index_dtype=torch.int32)
+
+        sc = cls(local_corpora, n_total, start, group=group, prepare=prepare, local_topk=local_topk,
+                 merge=lambda s, i, k: ops.merge_topk(s, i, k))
+        sc.n_local = sc.shard.n
+        return sc
 
     def topk(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global top-k over all shards: (scores f32 [Q,k'], global rows i64 [Q,k']), k' = min(k, n_total)."""

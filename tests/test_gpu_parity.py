@@ -368,6 +368,45 @@ def test_joint_fusion_fp8_and_errors(m):
         m.topk_joint([qs[0].cuda(), qs[1][:, :100].cuda()], jc, 5)
 
 
+# ------------------------------------------------------------------------------------------ corpus containers
+def test_streamed_prepare_and_corpus_files(m, tmp_path):
+    """Chunk-wise K1 gives bit-identical tiles to a one-shot prepare; the reference's corpus containers (h5-shaped
+    arrays as .npz/.npy, image-feature pickle dict) load into prepared corpora; rows=(lo,hi) loads one shard."""
+    import pickle
+    import numpy as np
+    c = _data("text", 5000, 768, 95)
+    whole = m.prepare_corpus(c.cuda(), dtype="bf16")
+    parts = [c[:1234], c[1234:1234], c[1234:4000].numpy(), c[4000:]]
+    st = m.prepare_streamed(parts, 5000, 768, dtype="bf16", keep_source=True)
+    assert torch.equal(st.rows, whole.rows) and torch.equal(st.inv_norm, whole.inv_norm) and torch.equal(st.source, c.cuda())
+    with pytest.raises(ValueError):
+        m.prepare_streamed([c[:10]], 11, 768)
+    # the text corpus layout of text2text_retrieval.py:146-155 (fp16 embeddings + ids), as npz / npy
+    ids = np.array([f"train_{j}".encode() for j in range(5000)])
+    np.savez(tmp_path / "train_embeddings.npz", embeddings=c.numpy().astype(np.float16), ids=ids)
+    np.save(tmp_path / "emb.npy", c.numpy().astype(np.float16))
+    pc, got_ids = m.load_text_corpus(str(tmp_path / "train_embeddings.npz"), chunk_rows=1500)
+    assert got_ids[17] == "train_17" and pc.n == 5000 and pc.source.dtype == torch.float16
+    q = _data("text", 50, 768, 96)
+    s, i = m.topk(q.cuda(), pc, 10)
+    full = exact.exact_scores(q, c.half().float())
+    assert exact.compare_topk(s, i, full, 10, tie_tol=2e-6).ok
+    shard, _ = m.load_text_corpus(str(tmp_path / "emb.npy"), rows=(2000, 3500), chunk_rows=700)
+    s2, i2 = m.topk(q.cuda(), shard, 10)
+    assert shard.idx_offset == 2000 and int(i2.min()) >= 2000 and int(i2.max()) < 3500
+    assert exact.compare_topk(s2.cpu(), i2.cpu() - 2000, full[:, 2000:3500], 10, tie_tol=2e-6).ok
+    # the image-feature pickle of im2im_retrieval.py:51-62
+    g = load_golden("im2im_a.npz")
+    fd = {f"data/evidence_corpus/{j}_evidence.jpg": v for j, v in enumerate(g["corpus_t"])}
+    with open(tmp_path / "evidence_features.pkl", "wb") as f:
+        pickle.dump(fd, f)
+    ipc, keys = m.load_image_corpus(str(tmp_path / "evidence_features.pkl"), chunk_rows=100)
+    assert keys == list(fd.keys()) and ipc.eps == 1e-6 and ipc.n == len(fd)
+    s3, i3 = m.topk(g["queries_t"].cuda(), ipc, 5)
+    full3 = exact.exact_scores(g["queries_t"], g["corpus_t"], "cos", 1e-6)
+    assert exact.compare_topk(s3, i3, full3, 5, tie_tol=2e-6).ok
+
+
 # ------------------------------------------------------------------------------------------ drop-in surfaces
 @pytest.mark.parametrize("name", ["im2im_a.npz", "im2im_b.npz"])
 def test_image_corpus_matches_reference_golden(m, name):
