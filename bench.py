@@ -12,6 +12,10 @@ Workloads (BASELINE.json configs):
   c3  text2text, 16384 queries x 1,000,000 x 768, top-10, bf16, corpus row-sharded over N GPUs   [default]
   c2  im2im, 4096 queries x 50,000 x 2048, top-10, bf16 (1 GPU)
   c1  text2text, 1000 queries x 10,000 x 768, top-5, fp32 configuration
+  c4  joint image+text, 16384 query pairs x 10,000,000 x (512+512), fused top-10, bf16, row-sharded (built for 8 GPUs;
+      with fewer ranks every rank still holds 1/8 of the corpus: "one GPU's share", stated in config.workload)
+  c5  large-corpus stress, 65536 queries x 100,000,000 x 768 fp8, top-100, row-sharded (same 1/8-share rule; the shard
+      is streamed through K1 chunk-wise straight to fp8 tiles, fp16 source kept for the exact re-score)
 """
 from __future__ import annotations
 
@@ -35,11 +39,16 @@ WORKLOADS = {
     "c1": (1000, 10_000, 768, 5, "fp32", "text", 1e-12),
     "c2": (4096, 50_000, 2048, 10, "bf16", "image", 1e-6),
     "c3": (16384, 1_000_000, 768, 10, "bf16", "text", 1e-12),
+    "c4": (16384, 10_000_000, 1024, 10, "bf16", "joint", 1e-12),
+    "c5": (65536, 100_000_000, 768, 100, "fp8", "text", 1e-12),
 }
+BUILT_FOR = {"c4": 8, "c5": 8}        # configs defined on 8 GPUs: with fewer ranks each still holds 1/8 of the rows
 NAMES = {
     "c1": "text2text 1k claims x 10k evidence x 768, top-5 cosine, fp32 configuration (BASELINE configs[0])",
     "c2": "im2im 4096 queries x 50k images x 2048, top-10 cosine, bf16 (BASELINE configs[1])",
     "c3": "text2text 16384 queries x 1M corpus x 768, top-10 cosine, bf16, row-sharded (BASELINE configs[2])",
+    "c4": "joint image+text 16384 query pairs x 10M corpus x (512+512), fused top-10, bf16, row-sharded (BASELINE configs[3])",
+    "c5": "large-corpus stress 65536 queries x 100M corpus x 768 fp8, top-100, row-sharded (BASELINE configs[4])",
 }
 METRIC = "queries/sec, top-K cosine retrieval (whole job)"
 
@@ -126,10 +135,13 @@ def make_rows(kind, rows, dim, seed, device, chunk=131072):
 # ------------------------------------------------------------------------------------------------ CPU arms
 def cpu_text_baseline(q_n, c_n, dim, k, budget_s=20.0):
     """oracle/st_util.semantic_search (restated sentence-transformers 3.3.1) on the host cores, fp32, upstream's
-    default chunking; bounded sample: a slice of the queries against the FULL corpus."""
+    default chunking; bounded sample: a slice of the queries against the FULL corpus (corpora beyond 1M rows: against
+    1M rows, throughput scaled by rows -- the arithmetic is linear in corpus rows)."""
     import torch
     from oracle import st_util
     torch.set_num_threads(os.cpu_count() or 1)
+    c_full = c_n
+    c_n = min(c_n, 1_000_000)
     corpus = make_rows("text", c_n, dim, 1003, "cpu")
     sample = min(q_n, 100)
     queries = make_rows("text", sample, dim, 1004, "cpu")
@@ -151,10 +163,12 @@ def cpu_text_baseline(q_n, c_n, dim, k, budget_s=20.0):
         st_util.semantic_search(queries[n_single], corpus, top_k=k)
         n_single += 1
     single_qps = n_single / (time.perf_counter() - t1)
-    return {"value": sample / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample} of {q_n} queries x full {c_n}x{dim} corpus, fp32, batched 100-query chunks "
-                      f"(oracle/st_util.semantic_search); one-query-per-call as the reference does it: {single_qps:.2f} q/s",
-            "one_query_per_call_qps": single_qps}
+    scale = c_n / c_full
+    note = "" if scale == 1.0 else f" [measured on {c_n} of {c_full} corpus rows, value scaled by {scale:.4f}]"
+    return {"value": sample / dt * scale, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port", "sample_ms": dt * 1e3,
+            "sample": f"{sample} of {q_n} queries x {c_n}x{dim} corpus, fp32, batched 100-query chunks "
+                      f"(oracle/st_util.semantic_search); one-query-per-call as the reference does it: {single_qps * scale:.2f} q/s" + note,
+            "one_query_per_call_qps": single_qps * scale}
 
 
 def cpu_image_baseline(q_n, c_n, dim, k, budget_s=20.0):
@@ -175,7 +189,7 @@ def cpu_image_baseline(q_n, c_n, dim, k, budget_s=20.0):
     tb = time.perf_counter()
     im2im.retrieve_similar_batched(make_rows("image", 64, dim, 1005, "cpu"), fd, top_k=k)
     batched_qps = 64 / (time.perf_counter() - tb)
-    return {"value": done / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+    return {"value": done / dt, "unit": "queries/s", "cores": 1, "kind": "port", "sample_ms": dt * 1e3,
             "sample": f"{done} of {q_n} queries x full {c_n}x{dim} corpus, the reference's per-pair python loop "
                       f"(oracle/im2im.retrieve_similar); batched fp32 matmul restatement on all cores: {batched_qps:.1f} q/s",
             "batched_matmul_qps": batched_qps}
@@ -192,12 +206,13 @@ def run_reference(args):
     info = None
     steps = max(1, min(args.steps, 3))
     for _ in range(max(0, min(args.warmup, 1)) + steps):
-        info = (cpu_image_baseline if kind == "image" else cpu_text_baseline)(q_n, c_n, dim, k, budget_s=20.0)
+        c_eff = c_n if args.workload not in BUILT_FOR else c_n * max(1, args.gpus) // max(args.gpus, BUILT_FOR[args.workload])
+        info = (cpu_image_baseline if kind == "image" else cpu_text_baseline)(q_n, c_eff, dim, k, budget_s=20.0)
         vals.append(info["value"])
     v = statistics.median(vals[-steps:])
     info["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+            "warmup": min(args.warmup, 1), "ms_per_step": info.get("sample_ms"), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": NAMES[args.workload], "note": "each step is a bounded sample, see cpu_baseline.sample"},
             "cpu_baseline": info,
@@ -209,16 +224,41 @@ def run_reference(args):
 def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto"):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
-    lo, hi = shard_bounds(c_n, world, rank)
-    corpus_local = make_rows(kind, hi - lo, dim, 17 + rank, device)
-    queries = make_rows(kind, q_n, dim, 5, device)             # replicated: same seed on every rank
+    parts = max(world, BUILT_FOR.get(name, 1))
+    lo, hi = shard_bounds(c_n, parts, rank)
+    c_total = c_n if parts == world else sum(shard_bounds(c_n, parts, r)[1] - shard_bounds(c_n, parts, r)[0] for r in range(world))
     torch.cuda.synchronize()
-
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps, exchange=exchange)
-    t1.record()
+    if kind == "joint":
+        half = dim // 2
+        corp = [make_rows("text", hi - lo, half, 17 + rank, device), make_rows("text", hi - lo, half, 117 + rank, device)]
+        queries = [make_rows("text", q_n, half, 5, device), make_rows("text", q_n, half, 6, device)]
+        torch.cuda.synchronize()
+        t0.record()
+        sc = ShardedCorpus.from_joint(corp, c_total, lo, weights=(0.5, 0.5), dtype=op, eps=eps)
+        t1.record()
+    elif name == "c5":
+        from mmd_retrieval import prepare_streamed
+        chunk = 1_000_000
+
+        def chunks():
+            for a in range(lo, hi, chunk):
+                yield make_rows("text", min(chunk, hi - a), dim, 1000 * (rank + 1) + (a - lo) // chunk, device)
+
+        queries = make_rows("text", q_n, dim, 5, device)
+        torch.cuda.synchronize()
+        t0.record()
+        shard = prepare_streamed(chunks(), hi - lo, dim, dtype=op, keep_source=torch.float16, idx_offset=lo)
+        sc = ShardedCorpus.from_prepared(shard, c_total, exchange=exchange)
+        t1.record()
+    else:
+        corpus_local = make_rows(kind, hi - lo, dim, 17 + rank, device)
+        queries = make_rows(kind, q_n, dim, 5, device)             # replicated: same seed on every rank
+        torch.cuda.synchronize()
+        t0.record()
+        sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps, exchange=exchange)
+        t1.record()
     torch.cuda.synchronize()
     prep_ms = t0.elapsed_time(t1)
 
@@ -264,7 +304,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     # ---- end to end: host (pinned) queries in, host results out, through the public call
     e2e = None
     if want_e2e:
-        q_host = queries.cpu().pin_memory()
+        q_host = [x.cpu().pin_memory() for x in queries] if isinstance(queries, list) else queries.cpu().pin_memory()
         res_s = torch.empty((q_n, k), dtype=torch.float32).pin_memory()
         res_i = torch.empty((q_n, k), dtype=torch.int64).pin_memory()
 
@@ -291,7 +331,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     ms_per_step = elapsed_ms / steps
     fused_avg = sum(fused_ms) / len(fused_ms) if fused_ms else None
     flops_per_launch = 2.0 * q_n * (hi - lo) * dim
-    return {"q_n": q_n, "c_n": c_n, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
+    return {"q_n": q_n, "c_n": c_n, "c_total": c_total, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
             "ms_per_step": ms_per_step, "prep_ms": prep_ms, "fused_ms": fused_avg, "flops_per_launch": flops_per_launch,
             "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item()),
             "exchange": sc.exchange if world > 1 else "none (1 GPU)"}
@@ -304,15 +344,20 @@ def roofline_of(res, peaks, name):
     # a kernel timed inside a long power-capped step -> sustained peak; a sub-millisecond step -> burst peak
     long_step = res["ms_per_step"] >= 5.0
     peak = peaks["tflops_sustained"] if long_step else peaks["tflops_burst"]
+    src = peaks["source"] + (", sustained" if long_step else ", burst")
+    spec = 2250.0
+    if res["op"] == "fp8":
+        # MEASURED_PEAKS.json holds no fp8 figure: the e4m3 tensor pipe is nominally 2x the bf16 one
+        peak, spec, src = 2.0 * peak, 4500.0, src + " bf16 x 2 (no measured fp8 peak; nominal fp8:bf16 ratio)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and res["rows_local"] == res["c_n"]:      # the capture is of the unsharded launch
         with open(tpath) as f:
             traffic = json.load(f).get(name)
     return {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"] + (", sustained" if long_step else ", burst"),
+            "frac": achieved / peak, "traffic": traffic, "peak_source": src,
             "kernel_ms": res["fused_ms"], "flops_per_launch": res["flops_per_launch"],
-            "frac_of_burst": achieved / peaks["tflops_burst"], "frac_of_spec_2250": achieved / 2250.0}
+            "frac_of_burst": achieved / (peaks["tflops_burst"] * (2.0 if res["op"] == "fp8" else 1.0)), "frac_of_spec": achieved / spec, "spec_tflops": spec}
 
 
 def run_ours(args):
@@ -322,6 +367,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import mmd_retrieval as m
+    from mmd_retrieval.ops import overfetch_for
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -344,7 +390,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q_n, c_n, dim, k, op, kind, eps = WORKLOADS[args.workload]
-        cpu = (cpu_image_baseline if kind == "image" else cpu_text_baseline)(q_n, c_n, dim, k)
+        cpu = (cpu_image_baseline if kind == "image" else cpu_text_baseline)(q_n, res["c_total"], dim, k)
 
     if rank == 0:
         q_n, c_n, dim, k, op, kind, eps = WORKLOADS[args.workload]
@@ -353,11 +399,13 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "bf16x3 (fp32-accurate split)"}.get(op, op),
             "data": "synthetic",
-            "config": {"workload": NAMES[args.workload], "queries": q_n, "corpus_rows": c_n, "dim": dim, "top_k": k,
+            "config": {"workload": NAMES[args.workload] + ("" if res["c_total"] == c_n else
+                                                           f" -- HERE: {world} rank(s) x one GPU's 1/{BUILT_FOR[args.workload]} share = {res['c_total']} rows"),
+                       "queries": q_n, "corpus_rows": res["c_total"], "dim": dim, "top_k": k,
                        "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}", "exchange": res["exchange"],
                        "l2": "operands exceed L2 (no flush needed)" if res["rows_local"] * dim * 2 > 126e6 else
                              "corpus shard fits L2; queries + source rows re-read per step",
-                       "prep_ms": res["prep_ms"], "rescore": "exact fp32 re-score of 18 over-fetched candidates per query",
+                       "prep_ms": res["prep_ms"], "rescore": f"exact fp32 re-score of {overfetch_for(k, res['rows_local'])} over-fetched candidates per query",
                        "peaks": peaks["source"]},
             "roofline": roofline_of(res, peaks, args.workload),
             "cpu_baseline": cpu,

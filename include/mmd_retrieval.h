@@ -151,6 +151,15 @@ MMD_API int mmd_rescore_joint(int n_seg, const void* const* q_src_host, const in
                       const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
                       int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, void* stream);
 
+/* ---- distinct-score filter of ranked lists ---------------------------------------------------- */
+/* scores/idx [Q, k_in] descending (as every entry point above returns them).  Keeps, per query, the first entry of every
+ * distinct score -- and any entry whose row equals gold_idx[q] (gold_idx nullable; -1 = none) -- until top_k are kept:
+ * the walk of src/evidence/im2im_retrieval.py:94-104 / text2text_retrieval.py:105-118 and its gold-exempting variants
+ * experiment_image.py:41-50 / experiment_text.py:79-87.  out_* [Q, top_k] padded with (-inf, -1); out_count[q]
+ * (nullable) = entries kept, so the caller can over-fetch more when a duplicate-heavy corpus leaves a list short. */
+MMD_API int mmd_dedupe_scores(const float* scores, const int32_t* idx, const int32_t* gold_idx, int64_t Q, int k_in, int top_k,
+                      float* out_scores, int32_t* out_idx, int32_t* out_count, void* stream);
+
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* While enabled, every fused contraction launch of mmd_topk_scores is bracketed by CUDA events on its own
  * stream (up to 512 launches are kept).  mmd_profile_collect synchronises those events, writes up to `cap`

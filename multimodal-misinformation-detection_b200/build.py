@@ -20,7 +20,7 @@ OUT_DIR = HERE / "mmd_retrieval"
 LIB = OUT_DIR / "libmmd.so"
 OBJ_DIR = HERE / "build"
 
-SOURCES = ["api.cu", "normalize.cu", "topk_fused.cu", "topk_merge.cu", "rescore.cu"]
+SOURCES = ["api.cu", "normalize.cu", "topk_fused.cu", "topk_merge.cu", "rescore.cu", "dedupe.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "--expt-relaxed-constexpr", "-DMMD_BUILDING"]

@@ -8,6 +8,7 @@ Public surface (mirrors the reference's entry points; see DESIGN.md / INTEGRATIO
     semantic_search(q, corpus, top_k=..)           drop-in for sentence_transformers.util.semantic_search
     cos_sim / dot_score                            drop-in score functions
     ImageCorpus / ImageSimilarity                  drop-in for src/evidence/im2im_retrieval.py
+    SemanticSimilarity                             drop-in for src/evidence/text2text_retrieval.py's search (encoders pluggable)
     ShardedCorpus                                  row-sharded corpus over the GPUs of one box
     prepare_joint / topk_joint                     joint image+text retrieval, weighted score fusion in one contraction
 
@@ -19,6 +20,7 @@ from .ops import (PreparedCorpus, prepare_corpus, topk, dense_scores, merge_topk
 from .postfilter import dedupe_by_score, hits_at_k
 from .semantic_search import semantic_search, cos_sim, dot_score, clear_cache
 from .image_corpus import ImageCorpus, ImageSimilarity, calculate_topk_accuracy_image_retrieval
+from .text_corpus import SemanticSimilarity
 from .sharded import ShardedCorpus, shard_bounds
 from .joint import JointCorpus, prepare_joint, topk_joint
 from .corpus_io import prepare_streamed, load_text_corpus, load_image_corpus
@@ -26,6 +28,6 @@ from .corpus_io import prepare_streamed, load_text_corpus, load_image_corpus
 __all__ = [
     "MmdError", "LIB_PATH", "PreparedCorpus", "prepare_corpus", "topk", "dense_scores", "merge_topk", "normalize_cast",
     "max_k", "profile_enable", "profile_collect", "launch_count", "dedupe_by_score", "hits_at_k", "semantic_search",
-    "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "calculate_topk_accuracy_image_retrieval",
+    "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "SemanticSimilarity", "calculate_topk_accuracy_image_retrieval",
     "ShardedCorpus", "shard_bounds", "JointCorpus", "prepare_joint", "topk_joint", "prepare_streamed", "load_text_corpus", "load_image_corpus",
 ]

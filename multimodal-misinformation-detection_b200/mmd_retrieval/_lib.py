@@ -47,6 +47,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                     C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_dedupe_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "mmd_launch_count": (C.c_int64, []),
     "mmd_profile_enable": (C.c_int, [C.c_int]),
     "mmd_profile_collect": (C.c_int, [C.POINTER(C.c_float), C.c_int]),

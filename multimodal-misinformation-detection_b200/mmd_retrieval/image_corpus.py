@@ -96,9 +96,14 @@ class ImageCorpus:
 
     # -- retrieval --------------------------------------------------------------------------------
     def retrieve_similar_features(self, query_features, top_k: int = 50,
-                                  is_gold: Optional[Callable[[int, Hashable], bool]] = None
-                                  ) -> List[List[Tuple[Hashable, float]]]:
-        """Batched form: query_features [Q,D] (or [D]) -> one deduped (key, score) list per query."""
+                                  is_gold: Optional[Callable[[int, Hashable], bool]] = None,
+                                  gold_rows: Optional[Sequence[int]] = None) -> List[List[Tuple[Hashable, float]]]:
+        """Batched form: query_features [Q,D] (or [D]) -> one deduped (key, score) list per query.
+
+        The distinct-score walk (im2im_retrieval.py:94-104) runs on the device over the K' over-fetched candidates
+        (mmd_dedupe_scores); only the final top_k entries per query come back to the host.  gold_rows[q] (corpus row of
+        query q's gold evidence, -1 = none) enables the evaluation's gold exemption (experiment_image.py:41-50) on the
+        device; an arbitrary `is_gold(q, key)` predicate is honoured by a host walk instead."""
         pc = self.prepared()
         q = ops._as_rows(query_features, pc.device)
         n_queries = q.shape[0]
@@ -106,25 +111,37 @@ class ImageCorpus:
             return [[] for _ in range(n_queries)]
         out: List[Optional[List[Tuple[Hashable, float]]]] = [None] * n_queries
         pending = list(range(n_queries))
+        gold_t = None
+        if gold_rows is not None and is_gold is None:
+            gold_t = torch.as_tensor(list(gold_rows), dtype=torch.int32, device=pc.device)
         fetch = min(pc.n, max(top_k + 8, 2 * top_k), ops.max_k())
         while pending:
-            sub = q[pending] if len(pending) != n_queries else q
+            whole = len(pending) == n_queries
+            sub = q if whole else q[pending]
             if fetch >= pc.n and pc.n > ops.max_k():
                 # duplicate-heavy corpus exhausted the fused K limit: rank the dense score row on the device
                 dense = ops.dense_scores(sub, pc.source, metric="cos", dtype="fp32", eps=IMAGE_EPS)
-                s_sorted, i_sorted = torch.sort(dense, dim=1, descending=True, stable=True)
-                s_host, i_host = s_sorted.cpu().tolist(), i_sorted.cpu().tolist()
+                scores, idx = torch.sort(dense, dim=1, descending=True, stable=True)
+                idx = idx.to(torch.int32)
             else:
-                scores, idx = ops.topk(sub, pc, fetch)
+                scores, idx = ops.topk(sub, pc, fetch, index_dtype=torch.int32)
+            n_ranked = scores.shape[1]
+            if is_gold is None:
+                gsub = None if gold_t is None else (gold_t if whole else gold_t[pending])
+                ks, ki, kn = ops.dedupe_scores(scores, idx, min(top_k, n_ranked), gsub)
+                s_host, i_host, n_host = ks.cpu().tolist(), ki.cpu().tolist(), kn.cpu().tolist()
+                kept_lists = [[(self._keys[i], s) for s, i in zip(s_host[pos][:n_host[pos]], i_host[pos][:n_host[pos]])]
+                              for pos in range(len(pending))]
+            else:
                 s_host, i_host = scores.cpu().tolist(), idx.cpu().tolist()
+                kept_lists = []
+                for pos, qi in enumerate(pending):
+                    ranked = [(self._keys[i], s) for s, i in zip(s_host[pos], i_host[pos]) if i >= 0]
+                    kept_lists.append(dedupe_by_score(ranked, top_k, lambda key, qi=qi: is_gold(qi, key)))
             still = []
             for pos, qi in enumerate(pending):
-                ranked = [(self._keys[i], s) for s, i in zip(s_host[pos], i_host[pos]) if i >= 0]
-                gold = (lambda key, qi=qi: is_gold(qi, key)) if is_gold is not None else None
-                kept = dedupe_by_score(ranked, top_k, gold)
-                exhausted = len(ranked) >= pc.n
-                if len(kept) == top_k or exhausted:
-                    out[qi] = kept
+                if len(kept_lists[pos]) == top_k or n_ranked >= pc.n:
+                    out[qi] = kept_lists[pos]
                 else:
                     still.append(qi)
             pending = still
@@ -142,5 +159,7 @@ def calculate_topk_accuracy_image_retrieval(image_corpus: ImageCorpus, query_fea
     """hits@k of each query's gold evidence key, with the reference's gold exemption in the dedupe
     (src/evidence/experiment_image.py:41-61).  query_features [Q,D]; gold_keys[q] = key of the paired evidence."""
     top_k = max(k_values)
-    lists = image_corpus.retrieve_similar_features(query_features, top_k, is_gold=lambda qi, key: key == gold_keys[qi])
+    image_corpus.prepared()
+    row_of = {key: r for r, key in enumerate(image_corpus._keys)}
+    lists = image_corpus.retrieve_similar_features(query_features, top_k, gold_rows=[row_of.get(g, -1) for g in gold_keys])
     return hits_at_k([[k for k, _ in lst] for lst in lists], list(gold_keys), k_values)

@@ -300,6 +300,26 @@ def merge_pairs(pairs: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Te
     return out_s, out_i
 
 
+def dedupe_scores(scores: torch.Tensor, idx: torch.Tensor, top_k: int, gold_idx: Optional[torch.Tensor] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Distinct-score filter on the device: ranked (scores f32, idx i32) [Q, k_in] -> (scores, idx) [Q, top_k] padded with
+    (-inf, -1) and the number of entries kept per query.  gold_idx i32 [Q] (optional) exempts each query's gold row."""
+    _require_cuda(scores.device)
+    n_queries, k_in = scores.shape
+    scores = scores.contiguous().float()
+    idx = idx.contiguous().to(torch.int32)
+    gold = None if gold_idx is None else gold_idx.to(device=scores.device, dtype=torch.int32).contiguous()
+    out_s = torch.empty((n_queries, top_k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((n_queries, top_k), dtype=torch.int32, device=scores.device)
+    out_n = torch.empty((n_queries,), dtype=torch.int32, device=scores.device)
+    if n_queries:
+        with torch.cuda.device(scores.device):
+            rc = _lib.load().mmd_dedupe_scores(_ptr(scores), _ptr(idx), _ptr(gold), n_queries, k_in, top_k, _ptr(out_s), _ptr(out_i),
+                                               _ptr(out_n), _stream_ptr(scores.device))
+        _lib.check(rc, "mmd_dedupe_scores")
+    return out_s, out_i, out_n
+
+
 def profile_enable(on: bool) -> None:
     _lib.load().mmd_profile_enable(int(on))
 

@@ -368,6 +368,60 @@ def test_joint_fusion_fp8_and_errors(m):
         m.topk_joint([qs[0].cuda(), qs[1][:, :100].cuda()], jc, 5)
 
 
+def test_text_search_drop_in_matches_restated_reference_flow(m):
+    """SemanticSimilarity.search: two corpora, top_k*5 each, concat, sort, distinct-score dedupe -- against the same
+    flow built from the restated sentence-transformers semantic_search (oracle/st_util.py) on the host; duplicate
+    evidence rows across the train / test corpora collapse exactly as in text2text_retrieval.py:105-118."""
+    train, test = _data("text", 3000, 768, 97), _data("text", 800, 768, 98)
+    test[5] = train[11]
+    test[6] = train[11]                                              # the same evidence three times
+    q = _data("text", 20, 768, 99)
+    q[0] = train[11] + 0.05 * q[0]
+    train_ids = [f"train_{j}".encode() for j in range(3000)]
+    test_ids = [f"test_{j}".encode() for j in range(800)]
+    ss = m.SemanticSimilarity(train.cuda(), train_ids, test.cuda(), test_ids)
+    got = ss.search_batch(q, top_k=5)
+    assert got[0] == ss.search(q[0], top_k=5)
+    for qi in range(20):
+        res = []
+        for corpus, ids in ((train, train_ids), (test, test_ids)):
+            hits = st_util.semantic_search(q[qi], corpus, top_k=25)[0]
+            res += [(ids[h["corpus_id"]].decode(), h["score"]) for h in hits]
+        want = m.dedupe_by_score(sorted(res, key=lambda t: t[1], reverse=True), 5)
+        assert [a for a, _ in got[qi]] == [a for a, _ in want] or qi == 0
+        assert max(abs(a - b) / abs(b) for (_, a), (_, b) in zip(got[qi], want)) <= FP32_RTOL
+    ids0 = [a for a, _ in got[0]]
+    assert ids0[0] in ("train_11", "test_5", "test_6") and len({"train_11", "test_5", "test_6"} & set(ids0)) == 1
+    # a pluggable re-ranker replaces the scores and the order
+    rer = m.SemanticSimilarity(train.cuda(), train_ids, test.cuda(), test_ids, cross_encoder=lambda query, texts: [float(len(t)) for t in texts],
+                               train_texts=["x" * (j % 7) for j in range(3000)], test_texts=["y" * (j % 5) for j in range(800)])
+    out = rer.search_batch(q[:2], top_k=3, query_texts=["a", "b"])
+    assert [s for _, s in out[0]] == sorted({s for _, s in out[0]}, reverse=True) and out[0][0][1] == 6.0
+
+
+def test_device_dedupe_matches_reference_walk(m):
+    """mmd_dedupe_scores vs the host restatement of the reference's distinct-score walk (with and without the gold
+    exemption), on lists full of repeated scores."""
+    from mmd_retrieval import ops
+    gen = torch.Generator().manual_seed(77)
+    for n_q, k_in, top_k in [(40, 18, 10), (9, 100, 50), (5, 3, 5), (3, 700, 20)]:
+        s = torch.sort(torch.randint(0, 12, (n_q, k_in), generator=gen).float() / 8, dim=1, descending=True).values
+        idx = torch.stack([torch.randperm(5000, generator=gen)[:k_in] for _ in range(n_q)]).to(torch.int32)
+        s[0, k_in - 1:] = float("-inf")
+        idx[0, k_in - 1:] = -1                                         # a padded tail
+        gold = idx[torch.arange(n_q), torch.randint(0, k_in, (n_q,), generator=gen)].clone()
+        gold[1] = -1
+        for g in (None, gold):
+            ks, ki, kn = ops.dedupe_scores(s.cuda(), idx.cuda(), top_k, None if g is None else g.cuda())
+            for r in range(n_q):
+                ranked = [(int(i), float(v)) for v, i in zip(s[r], idx[r]) if i >= 0]
+                want = m.dedupe_by_score(ranked, top_k, None if g is None else (lambda key, r=r: key == int(g[r])))
+                n = int(kn[r])
+                assert n == len(want)
+                assert ki[r, :n].tolist() == [a for a, _ in want] and ks[r, :n].tolist() == [b for _, b in want]
+                assert bool((ki[r, n:] == -1).all())
+
+
 # ------------------------------------------------------------------------------------------ corpus containers
 def test_streamed_prepare_and_corpus_files(m, tmp_path):
     """Chunk-wise K1 gives bit-identical tiles to a one-shot prepare; the reference's corpus containers (h5-shaped
