@@ -62,6 +62,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional c2 measurement at N=1")
+    ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
+                    help="replay the step from CUDA graphs (auto: if capture succeeds on every rank, else eager launches); "
+                         "measured equal to eager launches on C3/C2 (the GPU is never idle between kernels), so off by default")
+    ap.add_argument("--rescore", default="global", choices=["global", "local"],
+                    help="N>1: exact re-score after the global candidate merge (default) or per shard before the exchange")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how the per-rank top-K lists are exchanged (peer-memory stores from the re-score kernel, or NCCL all-gather)")
     return ap.parse_args()
@@ -221,7 +226,8 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto"):
+def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="off",
+                     rescore="global"):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
     parts = max(world, BUILT_FOR.get(name, 1))
@@ -250,14 +256,14 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         torch.cuda.synchronize()
         t0.record()
         shard = prepare_streamed(chunks(), hi - lo, dim, dtype=op, keep_source=torch.float16, idx_offset=lo)
-        sc = ShardedCorpus.from_prepared(shard, c_total, exchange=exchange)
+        sc = ShardedCorpus.from_prepared(shard, c_total, exchange=exchange, rescore=rescore)
         t1.record()
     else:
         corpus_local = make_rows(kind, hi - lo, dim, 17 + rank, device)
         queries = make_rows(kind, q_n, dim, 5, device)             # replicated: same seed on every rank
         torch.cuda.synchronize()
         t0.record()
-        sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps, exchange=exchange)
+        sc = ShardedCorpus(corpus_local, c_n, lo, dtype=op, metric="cos", eps=eps, exchange=exchange, rescore=rescore)
         t1.record()
     torch.cuda.synchronize()
     prep_ms = t0.elapsed_time(t1)
@@ -274,9 +280,39 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     torch.cuda.synchronize()
     barrier()
 
+    # ---- CUDA graphs: the whole step (every kernel + the exchange) recorded once, replayed per batch
+    m.profile_enable(True)            # before capture: the fused launch gets external event-record nodes in the graph
+    m.profile_collect()
+    graphed, graph_note, per_step_launches = None, "eager launches", None
+    if graph != "off" and kind != "joint":
+        ok = 1
+        try:
+            n_before = m.launch_count()
+            graphed = sc.capture(queries, k)
+            per_step_launches = (m.launch_count() - n_before) // max(1, len(graphed.graphs)) if world == 1 else None
+        except Exception as e:  # noqa: BLE001
+            ok, graph_note = 0, f"eager launches (graph capture failed: {type(e).__name__})"
+            if graph == "on":
+                raise
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            graphed = None
+        else:
+            graph_note = f"CUDA graph replay ({len(graphed.graphs)} graph(s))"
+            per_step_launches = graphed.launches_per_step
+
+            def step():                                            # noqa: F811
+                return graphed()
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            barrier()
+
     # ---- device-resident timed region
     n0 = m.launch_count()
-    m.profile_enable(True)
     m.profile_collect()
     sampler = ClockSampler(device.index)
     if rank == 0:
@@ -295,7 +331,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     elapsed_ms = e0.elapsed_time(e1)
     fused_ms = m.profile_collect()
     m.profile_enable(False)
-    launches = m.launch_count() - n0
+    launches = (m.launch_count() - n0) if graphed is None else per_step_launches * steps
     t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,7 +345,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         res_i = torch.empty((q_n, k), dtype=torch.int64).pin_memory()
 
         def e2e_step():
-            s, i = sc.topk(q_host, k)                           # H2D of the queries happens inside the call
+            s, i = graphed(q_host) if graphed is not None else sc.topk(q_host, k)   # H2D of the queries happens inside the call
             res_s.copy_(s, non_blocking=True)
             res_i.copy_(i, non_blocking=True)
             torch.cuda.synchronize()
@@ -334,7 +370,8 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     return {"q_n": q_n, "c_n": c_n, "c_total": c_total, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
             "ms_per_step": ms_per_step, "prep_ms": prep_ms, "fused_ms": fused_avg, "flops_per_launch": flops_per_launch,
             "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item()),
-            "exchange": sc.exchange if world > 1 else "none (1 GPU)"}
+            "exchange": sc.exchange if world > 1 else "none (1 GPU)", "launch_mode": graph_note,
+            "stage_order": (f"rescore after the global candidate merge" if rescore == "global" else "rescore per shard, one exchange") if world > 1 else "single shard"}
 
 
 def roofline_of(res, peaks, name):
@@ -380,7 +417,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     peaks = measured_peaks()
 
-    res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange)
+    res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange,
+                           graph=args.graph, rescore=args.rescore)
     extra = {}
     if world == 1 and not args.no_extra and args.workload != "c2":
         r2 = measure_workload(m, dist, torch, "c2", 1, 0, device, max(args.steps, 20), args.warmup)
@@ -402,7 +440,8 @@ def run_ours(args):
             "config": {"workload": NAMES[args.workload] + ("" if res["c_total"] == c_n else
                                                            f" -- HERE: {world} rank(s) x one GPU's 1/{BUILT_FOR[args.workload]} share = {res['c_total']} rows"),
                        "queries": q_n, "corpus_rows": res["c_total"], "dim": dim, "top_k": k,
-                       "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}", "exchange": res["exchange"],
+                       "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}", "exchange": res["exchange"], "launch_mode": res["launch_mode"],
+                       "stage_order": res["stage_order"],
                        "l2": "operands exceed L2 (no flush needed)" if res["rows_local"] * dim * 2 > 126e6 else
                              "corpus shard fits L2; queries + source rows re-read per step",
                        "prep_ms": res["prep_ms"], "rescore": f"exact fp32 re-score of {overfetch_for(k, res['rows_local'])} over-fetched candidates per query",

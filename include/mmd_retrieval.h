@@ -118,10 +118,17 @@ MMD_API int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtyp
 MMD_API int mmd_topk_merge(const float* scores, const int32_t* idx, int parts, int64_t Q, int k_in, int k_out,
                    float* out_scores, int32_t* out_idx, void* stream);
 
-/* Same merge over packed lists: pairs [parts, Q, k_in] of {int32 score bits (IEEE f32), int32 row} -- the layout
- * the all-gather of a row-sharded corpus moves (mmd_rescore_pairs writes it).  Lists need not be sorted. */
-MMD_API int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t Q, int k_in, int k_out, float* out_scores,
-                         int32_t* out_idx, void* stream);
+/* Same merge over packed lists: pairs [parts][Q, k_in] of {int32 score bits (IEEE f32), int32 row} -- the layout
+ * the exchange step of a row-sharded corpus moves (mmd_rescore_pairs / mmd_scatter_pairs write it).  Part p starts
+ * part_stride_pairs * p pairs after `pairs` (0 = Q * k_in, i.e. densely packed).  Lists need not be sorted. */
+MMD_API int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t part_stride_pairs, int64_t Q, int k_in, int k_out,
+                         float* out_scores, int32_t* out_idx, void* stream);
+
+/* Pack ranked lists (scores f32 [Q,k], idx i32 [Q,k]) into {score bits, row} pairs and store them to n_dst (1..16)
+ * destination buffers at pair offset dst_offset_pairs (dst_host: HOST array of DEVICE pointers, e.g. every peer's
+ * gather buffer): the candidate exchange of the row-sharded path when the exact re-score runs AFTER the global merge. */
+MMD_API int mmd_scatter_pairs(const float* scores, const int32_t* idx, int64_t Q, int k, void* const* dst_host, int n_dst,
+                      int64_t dst_offset_pairs, void* stream);
 
 /* ---- K5: exact re-score of the selected candidates ------------------------------------------ */
 /* For each query q and candidate j < k_in with cand_idx[q,j] >= 0 :
@@ -163,7 +170,9 @@ MMD_API int mmd_dedupe_scores(const float* scores, const int32_t* idx, const int
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* While enabled, every fused contraction launch of mmd_topk_scores is bracketed by CUDA events on its own
  * stream (up to 512 launches are kept).  mmd_profile_collect synchronises those events, writes up to `cap`
- * durations in milliseconds (oldest first), clears the list and returns how many it wrote. */
+ * durations in milliseconds (oldest first), clears the list and returns how many it wrote.  A launch recorded while
+ * the stream is being captured into a CUDA graph gets external event-record nodes instead: each later collect also
+ * reports the fused-kernel duration of that graph's most recent replay. */
 MMD_API int mmd_profile_enable(int on);
 MMD_API int mmd_profile_collect(float* ms_host, int cap);
 

@@ -716,7 +716,8 @@ namespace {
 struct Profile {
   std::mutex mu;
   bool on = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;         // eager launches: consumed by collect
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> graph_events;   // owned by captured graphs: kept, re-read every collect
 } g_profile;
 constexpr size_t kMaxProfiled = 512;
 
@@ -731,14 +732,21 @@ int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams
     attr_set = true;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  bool profiled = false;
+  bool profiled = false, capturing = false;
   {
     std::lock_guard<std::mutex> g(g_profile.mu);
-    if (g_profile.on && !kDense && g_profile.events.size() < kMaxProfiled) {
+    if (g_profile.on && !kDense && g_profile.events.size() + g_profile.graph_events.size() < kMaxProfiled) {
       if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) profiled = true;
     }
   }
-  if (profiled) cudaEventRecord(e0, stream);
+  if (profiled) {
+    // Under stream capture the bracket becomes two EXTERNAL event-record nodes of the graph: every replay re-records
+    // them, so after a replay the pair holds that replay's fused-kernel duration.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    capturing = cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+    if (capturing) cudaEventRecordWithFlags(e0, stream, cudaEventRecordExternal);
+    else cudaEventRecord(e0, stream);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
@@ -753,9 +761,10 @@ int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams
   cfg.numAttrs = 1;
   const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tq, tc, p, idesc);
   if (profiled) {
-    cudaEventRecord(e1, stream);
+    if (capturing) cudaEventRecordWithFlags(e1, stream, cudaEventRecordExternal);
+    else cudaEventRecord(e1, stream);
     std::lock_guard<std::mutex> g(g_profile.mu);
-    g_profile.events.emplace_back(e0, e1);
+    (capturing ? g_profile.graph_events : g_profile.events).emplace_back(e0, e1);
   }
   count_launch();
   MMD_CUDA_OK(le);
@@ -806,14 +815,18 @@ extern "C" int mmd_topk_max_k(void) { return 120; }
 extern "C" int mmd_profile_enable(int on) {
   std::lock_guard<std::mutex> g(mmd::g_profile.mu);
   mmd::g_profile.on = on != 0;
+  // switching off forgets the brackets that live inside captured graphs (the events stay alive: the graphs own nodes
+  // that reference them)
+  if (!mmd::g_profile.on) mmd::g_profile.graph_events.clear();
   return MMD_OK;
 }
 
 extern "C" int mmd_profile_collect(float* ms_host, int cap) {
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev, gev;
   {
     std::lock_guard<std::mutex> g(mmd::g_profile.mu);
     ev.swap(mmd::g_profile.events);
+    gev = mmd::g_profile.graph_events;
   }
   int n = 0;
   for (auto& pr : ev) {
@@ -825,6 +838,15 @@ extern "C" int mmd_profile_collect(float* ms_host, int cap) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
+  // brackets living inside captured graphs: the duration of each graph's most recent replay (if it has run)
+  for (auto& pr : gev) {
+    float ms = 0.0f;
+    if (cudaEventQuery(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess &&
+        ms_host != nullptr && n < cap) {
+      ms_host[n++] = ms;
+    }
+  }
+  cudaGetLastError();   // a never-replayed graph's events are "not recorded": not an error of the library
   return n;
 }
 

@@ -26,13 +26,14 @@ struct MergeSrc {
   const int32_t* idx;
   int parts, k_in;
   int64_t Q;
+  int64_t part_stride;    // pairs / entries between consecutive parts of the [parts][Q][k_in] layouts (>= Q * k_in)
 };
 
 __device__ __forceinline__ uint64_t load_candidate(const MergeSrc& s, int64_t q, int i) {
   if (i >= s.parts * s.k_in) return 0ull;
   if (s.keys != nullptr) return s.keys[q * (static_cast<int64_t>(s.parts) * s.k_in) + i];
   const int part = i / s.k_in, j = i - part * s.k_in;
-  const int64_t off = (static_cast<int64_t>(part) * s.Q + q) * s.k_in + j;
+  const int64_t off = static_cast<int64_t>(part) * s.part_stride + q * s.k_in + j;
   if (s.pairs != nullptr) {
     const int2 v = s.pairs[off];
     return v.y < 0 ? 0ull : make_key(__int_as_float(v.x), static_cast<uint32_t>(v.y));
@@ -236,6 +237,7 @@ int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, 
   src.parts = partial == nullptr ? 0 : parts;
   src.k_in = k_in;
   src.Q = Q;
+  src.part_stride = Q * k_in;
   if (partial == nullptr) {
     // no candidates at all: make load_candidate return "empty" for every slot
     src.keys = reinterpret_cast<const uint64_t*>(out_scores);   // never dereferenced (parts == 0)
@@ -266,17 +268,20 @@ extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts
   src.parts = parts;
   src.k_in = k_in;
   src.Q = Q;
+  src.part_stride = Q * k_in;
   return launch_merge<false>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t Q, int k_in, int k_out, float* out_scores,
-                                    int32_t* out_idx, void* stream) {
+extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t part_stride_pairs, int64_t Q, int k_in, int k_out,
+                                    float* out_scores, int32_t* out_idx, void* stream) {
   using namespace mmd;
   MMD_REQUIRE(parts > 0 && Q >= 0 && k_in > 0 && k_out > 0, "mmd_topk_merge_pairs: parts=%d Q=%lld k_in=%d k_out=%d", parts,
               (long long)Q, k_in, k_out);
   if (Q == 0) return MMD_OK;
   MMD_REQUIRE(pairs != nullptr && out_scores != nullptr && out_idx != nullptr, "mmd_topk_merge_pairs: null buffer");
   MMD_REQUIRE(reinterpret_cast<uintptr_t>(pairs) % 8 == 0, "mmd_topk_merge_pairs: pairs must be 8-byte aligned");
+  if (part_stride_pairs == 0) part_stride_pairs = Q * k_in;
+  MMD_REQUIRE(part_stride_pairs >= Q * k_in, "mmd_topk_merge_pairs: part stride %lld < Q*k_in", (long long)part_stride_pairs);
   MMD_REQUIRE((k_in <= 128 && k_out <= 128) || static_cast<int64_t>(parts) * k_in <= 4096,
               "mmd_topk_merge_pairs: parts*k_in = %lld exceeds 4096 (only lists of <= 128 entries stream)", (long long)parts * k_in);
   MMD_REQUIRE(k_out <= 4096, "mmd_topk_merge_pairs: k_out %d exceeds 4096", k_out);
@@ -290,5 +295,50 @@ extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t Q, int
   src.parts = parts;
   src.k_in = k_in;
   src.Q = Q;
+  src.part_stride = part_stride_pairs;
   return launch_merge<false>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- pack + scatter of ranked lists
+namespace mmd {
+namespace {
+constexpr int kMaxScatterDst = 16;
+struct ScatterDst {
+  int2* dst[kMaxScatterDst];
+  int n;
+  int64_t offset;
+};
+__global__ void __launch_bounds__(256)
+scatter_pairs_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int64_t total, ScatterDst d) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int2 v = make_int2(__float_as_int(scores[i]), idx[i]);
+    for (int t = 0; t < d.n; ++t) d.dst[t][d.offset + i] = v;
+  }
+}
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_scatter_pairs(const float* scores, const int32_t* idx, int64_t Q, int k, void* const* dst_host, int n_dst,
+                                 int64_t dst_offset_pairs, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(Q >= 0 && k > 0 && n_dst >= 1 && n_dst <= kMaxScatterDst && dst_offset_pairs >= 0,
+              "mmd_scatter_pairs: Q=%lld k=%d n_dst=%d", (long long)Q, k, n_dst);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(scores != nullptr && idx != nullptr && dst_host != nullptr, "mmd_scatter_pairs: null buffer");
+  int rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  ScatterDst d{};
+  d.n = n_dst;
+  d.offset = dst_offset_pairs;
+  for (int t = 0; t < n_dst; ++t) {
+    MMD_REQUIRE(dst_host[t] != nullptr && reinterpret_cast<uintptr_t>(dst_host[t]) % 8 == 0,
+                "mmd_scatter_pairs: destination %d is null or not 8-byte aligned", t);
+    d.dst[t] = static_cast<int2*>(dst_host[t]);
+  }
+  const int64_t total = Q * k;
+  const unsigned grid = static_cast<unsigned>(ceil_div(total, 256) < 2368 ? ceil_div(total, 256) : 2368);
+  scatter_pairs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, idx, total, d);
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
 }

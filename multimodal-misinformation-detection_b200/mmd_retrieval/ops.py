@@ -285,19 +285,55 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[tor
     return out_s, out_i
 
 
-def merge_pairs(pairs: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """K4 over packed lists: pairs int32 [parts, Q, k_in, 2] = {score bits, row} -> (scores f32, rows i32) [Q, k_out]."""
+def merge_pairs(pairs: torch.Tensor, k_out: int, n_queries: Optional[int] = None, k_in: Optional[int] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4 over packed lists -> (scores f32, rows i32) [Q, k_out].  pairs int32: either [parts, Q, k_in, 2] (dense), or
+    [parts, cap, 2] with the first Q * k_in pairs of every part in use (pass n_queries and k_in; parts are `cap` apart)."""
     _require_cuda(pairs.device)
-    parts, n_queries, k_in, two = pairs.shape
-    assert two == 2 and pairs.dtype == torch.int32 and pairs.is_contiguous()
+    assert pairs.dtype == torch.int32 and pairs.shape[-1] == 2 and pairs.is_contiguous()
+    if pairs.dim() == 4:
+        parts, n_queries, k_in, _ = pairs.shape
+        stride = n_queries * k_in
+    else:
+        parts, stride, _ = pairs.shape
+        assert n_queries is not None and k_in is not None and n_queries * k_in <= stride
     out_s = torch.empty((n_queries, k_out), dtype=torch.float32, device=pairs.device)
     out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=pairs.device)
     if n_queries:
         with torch.cuda.device(pairs.device):
-            rc = _lib.load().mmd_topk_merge_pairs(_ptr(pairs), parts, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
+            rc = _lib.load().mmd_topk_merge_pairs(_ptr(pairs), parts, stride, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
                                                   _stream_ptr(pairs.device))
         _lib.check(rc, "mmd_topk_merge_pairs")
     return out_s, out_i
+
+
+def merge_pairs_at(region: torch.Tensor, part_stride: int, k_out: int, n_queries: int, k_in: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """merge_pairs over a window of a larger gather buffer: `region` is a (non-contiguous) view whose first element is the
+    first pair of part 0; consecutive parts are part_stride pairs apart."""
+    _require_cuda(region.device)
+    parts = region.shape[0]
+    out_s = torch.empty((n_queries, k_out), dtype=torch.float32, device=region.device)
+    out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=region.device)
+    if n_queries:
+        with torch.cuda.device(region.device):
+            rc = _lib.load().mmd_topk_merge_pairs(_ptr(region), parts, part_stride, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
+                                                  _stream_ptr(region.device))
+        _lib.check(rc, "mmd_topk_merge_pairs")
+    return out_s, out_i
+
+
+def scatter_pairs(scores: torch.Tensor, idx: torch.Tensor, dst_ptrs: Sequence[int], dst_offset_pairs: int = 0) -> None:
+    """Pack ranked lists into {score bits, row} pairs and store them to every device pointer in dst_ptrs."""
+    _require_cuda(scores.device)
+    n_queries, k = scores.shape
+    if n_queries == 0:
+        return
+    assert scores.dtype == torch.float32 and idx.dtype == torch.int32 and scores.is_contiguous() and idx.is_contiguous()
+    arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    with torch.cuda.device(scores.device):
+        rc = _lib.load().mmd_scatter_pairs(_ptr(scores), _ptr(idx), n_queries, k, arr, len(dst_ptrs), int(dst_offset_pairs),
+                                           _stream_ptr(scores.device))
+    _lib.check(rc, "mmd_scatter_pairs")
 
 
 def dedupe_scores(scores: torch.Tensor, idx: torch.Tensor, top_k: int, gold_idx: Optional[torch.Tensor] = None

@@ -10,8 +10,14 @@ Scoring never crosses GPUs; the exchange is the path's only communication step. 
                    is still scoring other queries); one signal-pad barrier follows.  No collective launch.
   exchange="nccl"  K5 fills a local send buffer, one `all_gather_into_tensor` moves it.
 
-"auto" (default) uses "peer" when symmetric memory can be set up on every rank, else "nccl".  The reference has
-no counterpart (single process, single device).
+"auto" (default) uses "peer" when symmetric memory can be set up on every rank, else "nccl".
+
+Order of the stages (`rescore="global"`, the default): the tensor-core pass over-fetches K' candidates per shard; the
+K' raw lists are exchanged and merged FIRST, and only the global K' candidates are re-scored exactly -- each rank
+re-scores the candidates that live in its own shard (K'/world per query on average instead of K') and a second, smaller
+exchange + merge gives the final list.  `rescore="local"` re-scores every shard's K' candidates before a single exchange.
+`ShardedCorpus.capture()` records the whole step (all kernels and the exchange) in a CUDA graph for replay.
+The reference has no counterpart (single process, single device).
 
 `local_topk` / `merge` are injectable so the partition / offset / gather plumbing can be exercised with
 gloo on CPU (tests/test_sharded_gloo.py injects the CPU oracle there -- the product path below uses the
@@ -45,9 +51,10 @@ def _cuda_merge(scores, idx, k):
 class _PeerExchange:
     """Double-buffered gather buffers [2][world][cap pairs] in symmetric (peer-mapped) memory.
 
-    Step i writes into buffer i % 2 of every rank and then passes ONE barrier.  Reuse is safe without a second
-    barrier: a rank can only pass the barrier of step i after every peer has enqueued-and-finished its own stores of
-    step i, which in stream order come after that peer's merge of step i-1 -- the last reader of buffer (i+1) % 2."""
+    Step i uses buffer i % 2 of every rank; every exchange inside a step is "store to all peers, then ONE signal-pad
+    barrier".  Reuse without a barrier in front of the stores is safe: a rank passes the first barrier of step i only
+    after every peer has finished its own stores of step i, which in stream order come after that peer's last read of
+    step i-1 -- and the buffer written in step i+1 was last read in step i-1."""
 
     def __init__(self, group, world: int, cap_pairs: int, device: torch.device):
         import torch.distributed._symmetric_memory as symm_mem
@@ -57,14 +64,16 @@ class _PeerExchange:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.step = 0
 
-    def slot(self):
+    def slot(self, parity: Optional[int] = None):
         """(peer base pointers of this step's buffer, local view [world, cap, 2] of it)."""
-        b = self.step % 2
+        b = self.step % 2 if parity is None else parity
         off_bytes = b * self.world * self.cap * 2 * 4
         return [p + off_bytes for p in self.ptrs], self.buf[b]
 
-    def commit(self):
+    def barrier(self):
         self.hdl.barrier(channel=0)
+
+    def next_step(self):
         self.step += 1
 
 
@@ -72,7 +81,7 @@ class ShardedCorpus:
     """This rank's shard of a row-sharded corpus plus the collective that merges local top-K lists."""
 
     def __init__(self, local_rows, n_total: int, start: int, group=None, dtype: str = "bf16", metric: str = "cos",
-                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto",
+                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: str = "global",
                  local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, prepare: Optional[Callable] = None,
                  _shard=None):
         self.group = group
@@ -80,8 +89,12 @@ class ShardedCorpus:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = int(n_total)
         self.start = int(start)
+        self._max_local = -(-self.n_total // self.world)           # rows of the largest shard (balanced contiguous split)
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if rescore not in ("global", "local"):
+            raise ValueError("rescore must be 'global' or 'local'")
+        self.rescore = rescore
         self._exchange_req = exchange
         self.exchange = "nccl"            # what is actually in use; "peer" once symmetric memory is up on every rank
         self._peer: Optional[_PeerExchange] = None
@@ -110,9 +123,9 @@ class ShardedCorpus:
         return cls(corpus[lo:hi], corpus.shape[0], lo, group=group, **kw)
 
     @classmethod
-    def from_prepared(cls, shard, n_total: int, group=None, exchange: str = "auto") -> "ShardedCorpus":
+    def from_prepared(cls, shard, n_total: int, group=None, exchange: str = "auto", rescore: str = "global") -> "ShardedCorpus":
         """Wrap this rank's already prepared shard (e.g. corpus_io.prepare_streamed(..., idx_offset=start))."""
-        return cls(None, n_total, shard.idx_offset, group=group, exchange=exchange, _shard=shard)
+        return cls(None, n_total, shard.idx_offset, group=group, exchange=exchange, rescore=rescore, _shard=shard)
 
     @classmethod
     def from_joint(cls, local_corpora, n_total: int, start: int, weights=None, group=None, dtype: str = "bf16",
@@ -143,35 +156,73 @@ class ShardedCorpus:
             return ops.topk(queries, shard, k)
         if shard.source is None:
             return self._topk_generic(queries, k)
-        # local stage: K1 + fused tensor-core top-K' + strip merge, then the exact re-score writes this rank's
-        # k best as packed {score bits, global row} pairs straight into the all-gather's send buffer
         dev = shard.device
         q = ops._as_rows(queries, dev)
         n_queries = q.shape[0]
-        peer = self._peer_for(n_queries * k_glob, dev)
-        if peer is not None:
-            # K5 stores this rank's list into slot `rank` of EVERY rank's gather buffer (NVLink peer stores)
-            ptrs, gathered_flat = peer.slot()
-            dst, offset = ptrs, self.rank * peer.cap
-            gathered = gathered_flat[:, :n_queries * k_glob].view(self.world, n_queries, k_glob, 2)
-        else:
-            send = torch.empty((n_queries, k_glob, 2), dtype=torch.int32, device=dev)
-            dst, offset = [send.data_ptr()], 0
+        # every rank must exchange lists of one common width: the over-fetch of the LARGEST shard
+        kp_glob = ops.overfetch_for(min(k, self._max_local), self._max_local)
+        two_phase = self.rescore == "global"
+        cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
+        peer = self._peer_for(cap, dev)
+        return self._search(q, k, k_glob, kp_glob, peer, two_phase, peer.step % 2 if peer is not None else 0, advance=True)
+
+    def _search(self, q, k, k_glob, kp_glob, peer, two_phase, parity, advance):
+        """One search step on the current stream (eager or under CUDA-graph capture)."""
+        from . import ops
+        shard, dev, world, rank = self.shard, self.shard.device, self.world, self.rank
+        n_queries = q.shape[0]
         # (an empty shard goes through the same calls: every candidate is (-inf, -1))
-        q, q_inv, _, cand = ops.topk_candidates(q, shard, k)
-        ops.rescore_pairs(q, q_inv, shard, cand, k_glob, dst, dst_offset_pairs=offset)
+        qd, q_inv, raw_s, cand = ops.topk_candidates(q, shard, k, overfetch=kp_glob)
         if peer is not None:
-            peer.commit()                      # one signal-pad barrier: every peer's stores have landed
-            if gathered.is_contiguous():
-                s, i = ops.merge_pairs(gathered, k_glob)
-            else:
-                s, i = ops.merge_pairs(gathered.contiguous(), k_glob)
-            return s, i.to(torch.int64)
-        # NCCL: Q * k * 8 bytes per rank over NVLink
-        gathered = torch.empty((self.world, n_queries, k_glob, 2), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(gathered.view(self.world * n_queries, k_glob, 2), send, group=self.group)
-        s, i = ops.merge_pairs(gathered, k_glob)
+            ptrs, local = peer.slot(parity)                        # local: [world, cap, 2]
+
+        def exchange(fill, width, region_off):
+            """fill(dst_ptrs, pair_offset) stores this rank's [Q, width] list; returns the gathered [world] lists as
+            (tensor, layout) ready for merge_pairs."""
+            if peer is not None:
+                fill(ptrs, rank * peer.cap + region_off)
+                peer.barrier()                                     # every peer's stores have landed
+                region = local[:, region_off:, :]                  # parts are peer.cap pairs apart
+                if region_off == 0:
+                    return ("strided", local)
+                return ("strided_off", region)
+            send = torch.empty((n_queries, width, 2), dtype=torch.int32, device=dev)
+            fill([send.data_ptr()], 0)
+            gathered = torch.empty((world, n_queries, width, 2), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gathered.view(world * n_queries, width, 2), send, group=self.group)
+            return ("dense", gathered)
+
+        def merged(kind_t, width, k_out):
+            kind, t = kind_t
+            if kind == "dense":
+                return ops.merge_pairs(t, k_out)
+            if kind == "strided":
+                return ops.merge_pairs(t, k_out, n_queries=n_queries, k_in=width)
+            return ops.merge_pairs_at(t, peer.cap, k_out, n_queries, width)
+
+        if two_phase:
+            kp = cand.shape[1]
+            if kp < kp_glob:                                       # a small shard: pad its raw list to the common width
+                raw_s = torch.cat([raw_s, raw_s.new_full((n_queries, kp_glob - kp), float("-inf"))], dim=1).contiguous()
+                cand = torch.cat([cand, cand.new_full((n_queries, kp_glob - kp), -1)], dim=1).contiguous()
+            g1 = exchange(lambda d, off: ops.scatter_pairs(raw_s, cand, d, off), kp_glob, 0)
+            kc = min(world * kp_glob, ops.overfetch_for(k_glob, self.n_total))
+            _, cand_glob = merged(g1, kp_glob, kc)                 # the global K' candidates, identical on every rank
+            g2 = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand_glob, k_glob, d, dst_offset_pairs=off),
+                          k_glob, n_queries * kp_glob)
+            s, i = merged(g2, k_glob, k_glob)
+        else:
+            g = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand, k_glob, d, dst_offset_pairs=off), k_glob, 0)
+            s, i = merged(g, k_glob, k_glob)
+        if peer is not None and advance:
+            peer.next_step()
         return s, i.to(torch.int64)
+
+    def capture(self, queries, k: int) -> "GraphedSearch":
+        """Record the whole search step for `queries`' shape in CUDA graphs (one per exchange-buffer parity) and
+        return a callable that replays them: `s, i = graphed(new_queries)`; results live in static output buffers
+        until the next replay of the same parity."""
+        return GraphedSearch(self, queries, k)
 
     def _peer_for(self, n_pairs: int, dev: torch.device) -> Optional[_PeerExchange]:
         """Symmetric gather buffers big enough for n_pairs per rank, or None (-> NCCL).  Collective: every rank
@@ -222,3 +273,53 @@ class ShardedCorpus:
         i_all = gathered[..., 1].contiguous()
         s, i = self._merge(s_all, i_all, k_glob)
         return s, i.to(torch.int64)
+
+
+class GraphedSearch:
+    """A ShardedCorpus search step frozen into CUDA graphs (all kernels + the exchange), replayed per query batch."""
+
+    def __init__(self, sc: ShardedCorpus, queries, k: int):
+        from . import ops
+        if sc._injected or sc.shard.source is None:
+            raise RuntimeError("capture() needs the CUDA path with source embeddings kept (exact re-score)")
+        self.sc, self.k = sc, k
+        dev = sc.shard.device
+        q = ops._as_rows(queries, dev)
+        self.q_static = q.clone()
+        n_queries = q.shape[0]
+        k_glob = min(k, sc.n_total)
+        kp_glob = ops.overfetch_for(min(k, sc._max_local), sc._max_local)
+        two_phase = sc.rescore == "global" and sc.world > 1
+        self.peer = None
+        if sc.world > 1:
+            cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
+            sc.topk(self.q_static, k)                              # warm-up: lazy initialisation (attributes, symmetric memory)
+            if sc.exchange == "peer":
+                self.peer = _PeerExchange(sc.group, sc.world, cap, dev)      # this object's own double buffer
+        else:
+            ops.topk(self.q_static, sc.shard, k)
+        torch.cuda.synchronize(dev)
+        self.graphs, self.outs = [], []
+        self.launches_per_step = 0
+        n_graphs = 2 if self.peer is not None else 1
+        stream = torch.cuda.Stream(device=dev)
+        for parity in range(n_graphs):
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g, stream=stream):
+                if sc.world > 1:
+                    out = sc._search(self.q_static, k, k_glob, kp_glob, self.peer, two_phase, parity, advance=False)
+                else:
+                    out = ops.topk(self.q_static, sc.shard, k)
+            self.launches_per_step = ops.launch_count() - n0      # this library's kernels inside one replay
+            self.graphs.append(g)
+            self.outs.append(out)
+        self.calls = 0
+
+    def __call__(self, queries=None):
+        if queries is not None:
+            self.q_static.copy_(queries, non_blocking=True)
+        j = self.calls % len(self.graphs)
+        self.calls += 1
+        self.graphs[j].replay()
+        return self.outs[j]

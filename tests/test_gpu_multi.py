@@ -45,10 +45,21 @@ def _worker(rank, world, port, out):
         for _ in range(3):
             s2, i2 = sc.topk(queries, 10)
             assert torch.equal(i2, i) and torch.equal(s2, s)
-        # both exchange implementations give the same bits
-        sc_nccl = m.ShardedCorpus.from_full(corpus.cuda(), exchange="nccl")
-        s3, i3 = sc_nccl.topk(queries.cuda(), 10)
-        assert sc_nccl.exchange == "nccl" and torch.equal(i3, i) and torch.equal(s3, s)
+        # both exchange implementations and both stage orders give the same lists
+        for kw in ({"exchange": "nccl"}, {"rescore": "local"}, {"exchange": "nccl", "rescore": "local"}):
+            other = m.ShardedCorpus.from_full(corpus.cuda(), **kw)
+            s3, i3 = other.topk(queries.cuda(), 10)
+            assert other.exchange == kw.get("exchange", sc.exchange)
+            cmp3 = exact.compare_topk(s3, i3, full, 10, tie_tol=2e-6)
+            assert cmp3.ok and cmp3.max_rel_score_err <= 1e-5, (kw, cmp3)
+            assert torch.equal(i3, i) and torch.equal(s3, s), kw
+        # the whole step replayed from CUDA graphs (one per exchange-buffer parity), new queries copied in each time
+        graphed = sc.capture(queries.cuda(), 10)
+        for rep in range(4):
+            qq = queries if rep % 2 == 0 else queries.flip(0)
+            sg, ig = graphed(qq.cuda())
+            want_s, want_i = (s, i) if rep % 2 == 0 else (s.flip(0), i.flip(0))
+            assert torch.equal(ig, want_i) and torch.equal(sg, want_s), rep
         # fewer corpus rows than ranks * k: short and empty local lists are padded with (-inf, -1)
         tiny = m.ShardedCorpus.from_full(corpus[:5].cuda())
         s4, i4 = tiny.topk(queries.cuda(), 10)

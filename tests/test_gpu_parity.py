@@ -297,6 +297,21 @@ def test_sharded_equals_unsharded(m):
     assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
 
 
+def test_cuda_graph_replay_single_gpu(m):
+    """ShardedCorpus.capture on one GPU: the whole step (K1, fused top-K', strip merge, re-score) replayed from a CUDA
+    graph gives the same bits as the eager call, for fresh query batches copied into the static input."""
+    q, c = _data("text", 300, 768, 62), _data("text", 9000, 768, 63)
+    sc = m.ShardedCorpus(c.cuda(), 9000, 0)
+    want_s, want_i = sc.topk(q.cuda(), 10)
+    graphed = sc.capture(q.cuda(), 10)
+    for rep in range(3):
+        qq = q if rep != 1 else q.flip(0)
+        s, i = graphed(qq.cuda())
+        torch.cuda.synchronize()
+        ws, wi = (want_s, want_i) if rep != 1 else (want_s.flip(0), want_i.flip(0))
+        assert torch.equal(i, wi) and torch.equal(s, ws)
+
+
 def test_packed_pairs_exchange_layout(m):
     """The row-sharded path's exchange format on one GPU: every 'rank' re-scores its shard straight into its slot of a
     [world, Q, k] gather buffer of {score bits, global row} pairs (two destination buffers at once, as with
