@@ -21,6 +21,12 @@ tail -c 600 "$OUT/bench_n1.json"
 if [ -z "$QUICK" ]; then
   python bench.py --impl reference --steps 1 --warmup 0 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
   echo "ref rc=$?"
+  # the other BASELINE configs (c4 / c5: one GPU's 1/8 share of the 8-GPU configuration)
+  for wl in c1 c2 c4 c5; do
+    python bench.py --workload $wl --steps 10 --warmup 3 --no-extra > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
+    echo "bench $wl rc=$?"
+  done
+  python tools/gpu_diag.py perf2 k1perf > "$OUT/diag_perf.log" 2>&1
 fi
 
 SHORT="--steps 2 --warmup 1 --no-cpu-baseline --no-extra"

@@ -104,7 +104,8 @@ def main():
                     vals = [t["dram_read_bytes"] + t["dram_write_bytes"] for t in tr if t["dram_read_bytes"] is not None]
                     if vals:
                         traffic_json[wl] = sum(vals) / len(vals)
-        if name in ("bench_n1.json", "bench_ref.json", "pytest_gpu.log", "smoke.log"):
+        if name in ("bench_n1.json", "bench_ref.json", "pytest_gpu.log", "smoke.log", "diag_perf.log") or \
+                (name.startswith("bench_c") and name.endswith(".json")):
             with open(p) as fi, open(os.path.join(dst, f"{rnd}_{name}"), "w") as fo:
                 fo.write(fi.read())
     json.dump(traffic_json, open(tpath, "w"), indent=1)
