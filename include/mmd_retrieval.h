@@ -120,9 +120,11 @@ MMD_API int mmd_topk_merge(const float* scores, const int32_t* idx, int parts, i
 
 /* Same merge over packed lists: pairs [parts][Q, k_in] of {int32 score bits (IEEE f32), int32 row} -- the layout
  * the exchange step of a row-sharded corpus moves (mmd_rescore_pairs / mmd_scatter_pairs write it).  Part p starts
- * part_stride_pairs * p pairs after `pairs` (0 = Q * k_in, i.e. densely packed).  Lists need not be sorted. */
+ * part_stride_pairs * p pairs after `pairs` (0 = Q * k_in, i.e. densely packed).  parts_sorted != 0 promises that every
+ * list is already in (score descending, row ascending) order with its empty slots last -- what mmd_rescore_pairs and
+ * mmd_topk_scores produce -- and skips the per-list sort; 0 accepts lists in any order. */
 MMD_API int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t part_stride_pairs, int64_t Q, int k_in, int k_out,
-                         float* out_scores, int32_t* out_idx, void* stream);
+                         int parts_sorted, float* out_scores, int32_t* out_idx, void* stream);
 
 /* Pack ranked lists (scores f32 [Q,k], idx i32 [Q,k]) into {score bits, row} pairs and store them to n_dst (1..16)
  * destination buffers at pair offset dst_offset_pairs (dst_host: HOST array of DEVICE pointers, e.g. every peer's

@@ -273,7 +273,7 @@ extern "C" int mmd_topk_merge(const float* scores, const int32_t* idx, int parts
 }
 
 extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t part_stride_pairs, int64_t Q, int k_in, int k_out,
-                                    float* out_scores, int32_t* out_idx, void* stream) {
+                                    int parts_sorted, float* out_scores, int32_t* out_idx, void* stream) {
   using namespace mmd;
   MMD_REQUIRE(parts > 0 && Q >= 0 && k_in > 0 && k_out > 0, "mmd_topk_merge_pairs: parts=%d Q=%lld k_in=%d k_out=%d", parts,
               (long long)Q, k_in, k_out);
@@ -296,6 +296,8 @@ extern "C" int mmd_topk_merge_pairs(const void* pairs, int parts, int64_t part_s
   src.k_in = k_in;
   src.Q = Q;
   src.part_stride = part_stride_pairs;
+  // lists this library produced are already descending: skip the per-part sort (lists longer than 128 are always sorted)
+  if (parts_sorted) return launch_merge<true>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
   return launch_merge<false>(src, k_out, 1.0f, 0, out_scores, out_idx, static_cast<cudaStream_t>(stream));
 }
 

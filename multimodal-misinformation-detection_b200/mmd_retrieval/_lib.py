@@ -37,7 +37,8 @@ SIGNATURES = {
     "mmd_rescore": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                               C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                               C.c_void_p, C.c_void_p]),
-    "mmd_topk_merge_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_topk_merge_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "mmd_scatter_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p]),
     "mmd_rescore_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                     C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int,

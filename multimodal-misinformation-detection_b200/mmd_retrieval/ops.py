@@ -285,8 +285,8 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[tor
     return out_s, out_i
 
 
-def merge_pairs(pairs: torch.Tensor, k_out: int, n_queries: Optional[int] = None, k_in: Optional[int] = None
-                ) -> Tuple[torch.Tensor, torch.Tensor]:
+def merge_pairs(pairs: torch.Tensor, k_out: int, n_queries: Optional[int] = None, k_in: Optional[int] = None,
+                parts_sorted: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """K4 over packed lists -> (scores f32, rows i32) [Q, k_out].  pairs int32: either [parts, Q, k_in, 2] (dense), or
     [parts, cap, 2] with the first Q * k_in pairs of every part in use (pass n_queries and k_in; parts are `cap` apart)."""
     _require_cuda(pairs.device)
@@ -301,13 +301,14 @@ def merge_pairs(pairs: torch.Tensor, k_out: int, n_queries: Optional[int] = None
     out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=pairs.device)
     if n_queries:
         with torch.cuda.device(pairs.device):
-            rc = _lib.load().mmd_topk_merge_pairs(_ptr(pairs), parts, stride, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
-                                                  _stream_ptr(pairs.device))
+            rc = _lib.load().mmd_topk_merge_pairs(_ptr(pairs), parts, stride, n_queries, k_in, k_out, int(parts_sorted), _ptr(out_s),
+                                                  _ptr(out_i), _stream_ptr(pairs.device))
         _lib.check(rc, "mmd_topk_merge_pairs")
     return out_s, out_i
 
 
-def merge_pairs_at(region: torch.Tensor, part_stride: int, k_out: int, n_queries: int, k_in: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def merge_pairs_at(region: torch.Tensor, part_stride: int, k_out: int, n_queries: int, k_in: int,
+                   parts_sorted: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """merge_pairs over a window of a larger gather buffer: `region` is a (non-contiguous) view whose first element is the
     first pair of part 0; consecutive parts are part_stride pairs apart."""
     _require_cuda(region.device)
@@ -316,8 +317,8 @@ def merge_pairs_at(region: torch.Tensor, part_stride: int, k_out: int, n_queries
     out_i = torch.empty((n_queries, k_out), dtype=torch.int32, device=region.device)
     if n_queries:
         with torch.cuda.device(region.device):
-            rc = _lib.load().mmd_topk_merge_pairs(_ptr(region), parts, part_stride, n_queries, k_in, k_out, _ptr(out_s), _ptr(out_i),
-                                                  _stream_ptr(region.device))
+            rc = _lib.load().mmd_topk_merge_pairs(_ptr(region), parts, part_stride, n_queries, k_in, k_out, int(parts_sorted), _ptr(out_s),
+                                                  _ptr(out_i), _stream_ptr(region.device))
         _lib.check(rc, "mmd_topk_merge_pairs")
     return out_s, out_i
 

@@ -157,7 +157,7 @@ class ShardedCorpus:
         if shard.source is None:
             return self._topk_generic(queries, k)
         dev = shard.device
-        q = ops._as_rows(queries, dev)
+        q = self.upload_queries(queries)
         n_queries = q.shape[0]
         # every rank must exchange lists of one common width: the over-fetch of the LARGEST shard
         kp_glob = ops.overfetch_for(min(k, self._max_local), self._max_local)
@@ -165,6 +165,35 @@ class ShardedCorpus:
         cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
         peer = self._peer_for(cap, dev)
         return self._search(q, k, k_glob, kp_glob, peer, two_phase, peer.step % 2 if peer is not None else 0, advance=True)
+
+    def upload_queries(self, queries, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host-resident query batch (the SAME on every rank) -> device.  With more than one rank each rank uploads only its
+        1/world slice over PCIe and the slices are all-gathered over NVLink, instead of every rank pulling the whole batch
+        through the host's memory system: 8 x 50 MB per step at C3 otherwise.  Device tensors pass through."""
+        from . import ops
+        dev = self.shard.device
+        if (isinstance(queries, torch.Tensor) and queries.is_cuda) or self.world == 1 or self._injected:
+            q = ops._as_rows(queries, dev)
+            if out is not None:
+                out.copy_(q, non_blocking=True)
+                return out
+            return q
+        q_host = ops._as_rows(queries)
+        n_queries, dim = q_host.shape
+        per = -(-n_queries // self.world)
+        lo = min(n_queries, self.rank * per)
+        hi = min(n_queries, lo + per)
+        mine = torch.zeros((per, dim), dtype=q_host.dtype, device=dev) if hi - lo < per else \
+            torch.empty((per, dim), dtype=q_host.dtype, device=dev)
+        if hi > lo:
+            mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+        full = torch.empty((self.world * per, dim), dtype=q_host.dtype, device=dev)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        q = full[:n_queries]
+        if out is not None:
+            out.copy_(q, non_blocking=True)
+            return out
+        return q
 
     def _search(self, q, k, k_glob, kp_glob, peer, two_phase, parity, advance):
         """One search step on the current stream (eager or under CUDA-graph capture)."""
@@ -194,11 +223,12 @@ class ShardedCorpus:
 
         def merged(kind_t, width, k_out):
             kind, t = kind_t
+            # every list in flight was produced sorted by this library (strip merge / re-score): no per-list sort
             if kind == "dense":
-                return ops.merge_pairs(t, k_out)
+                return ops.merge_pairs(t, k_out, parts_sorted=True)
             if kind == "strided":
-                return ops.merge_pairs(t, k_out, n_queries=n_queries, k_in=width)
-            return ops.merge_pairs_at(t, peer.cap, k_out, n_queries, width)
+                return ops.merge_pairs(t, k_out, n_queries=n_queries, k_in=width, parts_sorted=True)
+            return ops.merge_pairs_at(t, peer.cap, k_out, n_queries, width, parts_sorted=True)
 
         if two_phase:
             kp = cand.shape[1]
@@ -318,7 +348,7 @@ class GraphedSearch:
 
     def __call__(self, queries=None):
         if queries is not None:
-            self.q_static.copy_(queries, non_blocking=True)
+            self.sc.upload_queries(queries, out=self.q_static)
         j = self.calls % len(self.graphs)
         self.calls += 1
         self.graphs[j].replay()

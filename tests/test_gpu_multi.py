@@ -53,6 +53,10 @@ def _worker(rank, world, port, out):
             cmp3 = exact.compare_topk(s3, i3, full, 10, tie_tol=2e-6)
             assert cmp3.ok and cmp3.max_rel_score_err <= 1e-5, (kw, cmp3)
             assert torch.equal(i3, i) and torch.equal(s3, s), kw
+        # host-resident queries: every rank uploads a 1/world slice and the slices are all-gathered (odd sizes too)
+        for n_q in (300, 299, 3, 1):
+            up = sc.upload_queries(queries[:n_q])
+            assert up.is_cuda and torch.equal(up.cpu(), queries[:n_q])
         # the whole step replayed from CUDA graphs (one per exchange-buffer parity), new queries copied in each time
         graphed = sc.capture(queries.cuda(), 10)
         for rep in range(4):
