@@ -96,12 +96,21 @@ __host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta) 
 }
 
 // ---------------------------------------------------------------- warp-cooperative list maintenance
-// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + ((r ^ slot) & 31)]: conflict-free both
-// when the 32 row-owner lanes touch the same slot of their own rows and when the whole warp reads one row.
-__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + ((r ^ slot) & 31); }
-// byte address (shared window) of slot `slot` of the row owned by `lane`
-__device__ __forceinline__ uint32_t key_slot_addr(uint32_t wkeys_addr, int slot, int lane) {
-  return wkeys_addr + static_cast<uint32_t>(slot) * 256u + ((static_cast<uint32_t>(lane ^ slot) & 31u) << 3);
+// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + r], as a RAW entry {lo = ~column, hi = fp32 score bits}:
+// an append is then four instructions (compare, address, predicated 8-byte store, predicated count) with no
+// bank conflicts for any mix of per-row counts (slots are 256 B apart, a multiple of the 128 B bank cycle).  Entries
+// become ordered keys only when a row is compacted; the warp-wide read of one row there is a 32-way bank conflict,
+// paid twice per compaction instead of once per appended score.
+__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + r; }
+__device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) {
+  return raw == 0ull ? 0ull
+                     : (static_cast<uint64_t>(float_to_ordered(__uint_as_float(static_cast<uint32_t>(raw >> 32)))) << 32) |
+                           (raw & 0xffffffffull);
+}
+__device__ __forceinline__ uint64_t key_to_raw(uint64_t key) {
+  return key == 0ull ? 0ull
+                     : (static_cast<uint64_t>(__float_as_uint(ordered_to_float(static_cast<uint32_t>(key >> 32)))) << 32) |
+                           (key & 0xffffffffull);
 }
 
 // R rows at a time go through the same bitonic network (independent dependency chains: one epilogue warp per
@@ -157,10 +166,10 @@ struct RowState {
 //   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
 // Returns the calling lane's own (count, threshold): a compacted row holds min(n, kprime) entries and, once it
 // holds kprime, its threshold is at least its kprime-th best score.
-template <int CAP, bool FINAL, int R>
+template <int CAP, bool FINAL, int R, int E>
 __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int& cnt,
                                               float& thr, uint64_t* out_rows, int64_t out_row_stride) {
-  constexpr int E = CAP / 32;
+  // E = registers per lane and row (CAP / 32)
   uint64_t k[R][E];
   int n[R];
 #pragma unroll
@@ -169,7 +178,7 @@ __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = e * 32 + lane;
-      k[r][e] = (i < n[r]) ? wkeys[key_slot_index(i, rows[r])] : 0ull;
+      k[r][e] = (i < n[r]) ? raw_to_key(wkeys[key_slot_index(i, rows[r])]) : 0ull;
     }
   }
   bitonic_sort_desc<E, R>(k, lane);
@@ -181,7 +190,7 @@ __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
-        if (i < keep) wkeys[key_slot_index(i, rows[r])] = k[r][e];
+        if (i < keep) wkeys[key_slot_index(i, rows[r])] = key_to_raw(k[r][e]);
       }
     } else {
       uint64_t* out = out_rows + static_cast<int64_t>(rows[r]) * out_row_stride;
@@ -206,6 +215,7 @@ template <int CAP, bool FINAL>
 __device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int cnt, float thr,
                                               uint64_t* out_rows, int64_t out_row_stride) {
   constexpr int R = CAP == 64 ? 4 : 2;
+  constexpr int E = CAP / 32;
   __syncwarp();
   while (__popc(mask) >= R) {
     int rows[R];
@@ -214,13 +224,13 @@ __device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, in
       rows[r] = __ffs(mask) - 1;
       mask &= mask - 1;
     }
-    compact_batch<CAP, FINAL, R>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+    compact_batch<CAP, FINAL, R, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
   }
   while (mask) {
     int rows[1];
     rows[0] = __ffs(mask) - 1;
     mask &= mask - 1;
-    compact_batch<CAP, FINAL, 1>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+    compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
   }
   __syncwarp();
   RowState st;
@@ -399,7 +409,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(warp - 2) * (CAP * 32);
-    const uint32_t wkeys_addr = smem_u32(wkeys);
+    const uint32_t row_addr = smem_u32(wkeys) + static_cast<uint32_t>(lane) * 8u;   // slot 0 of this thread's own row
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
@@ -531,13 +541,13 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 thr = st.thr;
                 if (thr != before) publish_threshold(p.thr_global, qrow, thr);
               }
-              // branch-free appends: key = (ordered score << 32) | ~column, stored under a predicate
+              // branch-free appends: raw entry {~column, score bits} stored under a predicate
               const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float x = v[g * 8 + j];
                 const bool take = x > thr;
-                st_shared_v2_pred(key_slot_addr(wkeys_addr, cnt, lane), ncol - j, float_to_ordered(x), take);
+                st_shared_v2_pred(row_addr + static_cast<uint32_t>(cnt) * 256u, ncol - j, __float_as_uint(x), take);
                 cnt += take ? 1 : 0;
               }
             }
