@@ -62,9 +62,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional c2 measurement at N=1")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step from CUDA graphs (auto: if capture succeeds on every rank, else eager launches): equal to "
-                         "eager launches while a step is long (1-2 GPUs), immune to host launch jitter when it is ~2.5 ms (8 GPUs)")
+    ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
+                    help="replay the step from CUDA graphs (auto: if capture succeeds on every rank, else eager launches).  Measured "
+                         "equal to eager launches at 1, 2 and 8 GPUs (the GPU never idles between kernels), hence off by default")
     ap.add_argument("--rescore", default="global", choices=["global", "local"],
                     help="N>1: exact re-score after the global candidate merge (default) or per shard before the exchange")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
@@ -226,7 +226,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="auto",
+def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="off",
                      rescore="global"):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]

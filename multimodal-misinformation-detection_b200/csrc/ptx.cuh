@@ -36,9 +36,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -112,14 +109,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Device
 }
 
 // ---------------------------------------------------------------- shared-memory accesses by window address
-__device__ __forceinline__ uint64_t ld_shared_u64(uint32_t addr) {
-  uint64_t v;
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_shared_u64(uint32_t addr, uint64_t v) {
-  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-}
 // {lo, hi} -> 8 bytes at addr, only where pred holds (no branch)
 __device__ __forceinline__ void st_shared_v2_pred(uint32_t addr, uint32_t lo, uint32_t hi, bool pred) {
   asm volatile(
@@ -133,17 +122,6 @@ __device__ __forceinline__ void st_shared_v2_pred(uint32_t addr, uint32_t lo, ui
 }
 
 // ---------------------------------------------------------------- elect / misc
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -165,7 +143,6 @@ __device__ __forceinline__ uint32_t mapa_shared_cluster(uint32_t addr, uint32_t 
 
 // ---------------------------------------------------------------- TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

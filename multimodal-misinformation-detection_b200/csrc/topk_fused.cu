@@ -12,9 +12,10 @@
 //   warp 0 (one lane)  TMA producer: {128 queries x 128 B} and {256 corpus rows x 128 B} boxes, 128B swizzle,
 //                      multi-stage ring of mbarriers.
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma 128x256x(32 B) into one of two 256-column TMEM accumulators.
-//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> query row.  A register
-//                      threshold (the row's current K-th best) filters 32 scores with a max tree and one
-//                      vote; survivors are appended to a per-row candidate buffer in shared memory which
+//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> query row.  Per tile a branch-free
+//                      FILTER pass (chunk maxima against the row thresholds, TMEM loads software pipelined) marks the
+//                      chunks worth a second look; a COLLECT pass re-reads only those and appends scores above the
+//                      row's threshold to a per-row candidate buffer in shared memory (predicated stores), which
 //                      the warp compacts with a shuffle bitonic sort when it fills.
 // Work decomposition: unit = (128-query tile, strip of T corpus tiles), query tile fastest so that the
 // CTAs running at the same time read the same corpus rows (L2 reuse; HBM sees the corpus ~once).
@@ -75,8 +76,6 @@ struct FusedParams {
 #else
 #define MMD_TRACE(tile, slot) do { } while (0)
 #endif
-#define MMD_STAT_BEGIN() do { } while (0)
-#define MMD_STAT_END(slot) do { } while (0)
 
 struct SmemLayout {
   uint32_t stage_off;    // stages x {A,B}
@@ -347,7 +346,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int t = t0; t < t1; ++t) {
           const int c_row = t * kTileN + static_cast<int>(cta_rank) * kBRows;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            { MMD_STAT_BEGIN(); mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1); MMD_STAT_END(0); }
+            mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1);
             uint8_t* sa = smem + L.stage_off + stage * kStageBytes;
             const int kelem = kb * (kF8 ? kBlockKBytes : kBlockKBytes / 2);
             if constexpr (kCta == 1) {
@@ -383,7 +382,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kTileN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            { MMD_STAT_BEGIN(); mbar_wait(&full_bar[stage], phase, p.status, 3); MMD_STAT_END(2); }
+            mbar_wait(&full_bar[stage], phase, p.status, 3);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + L.stage_off + stage * kStageBytes);
             const uint64_t adesc = make_smem_desc_sw128(sa);
