@@ -107,6 +107,20 @@ MMD_API int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype
                     int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Row-sharded corpora: same call, but the per-query pruning thresholds live in caller-owned arrays shared by ALL ranks.
+ * thr_local = this rank's array (uint32 [Q], zeroed by the caller before the step on every rank, with a barrier between
+ * the zeroing and the first launch); thr_all_host = HOST array of n_thr (1..8) DEVICE pointers to every rank's array (own one
+ * included; peer-mapped memory).  A shard's K-th best score is a lower bound of the global K-th best, so every bound a
+ * CTA learns is published to all ranks with system-scope atomics over NVLink and prunes every shard.  The lists returned
+ * then hold each shard's candidates for the GLOBAL top-k (possibly fewer than k valid entries), not its complete local
+ * top-k; the merged global top-k is unchanged.  pair_dst_host (n_pair_dst = 0..16 device pointers, may be NULL/0):
+ * the strip merge additionally stores the list as packed {score bits, row} pairs at pair offset pair_offset + q * k + rank
+ * into every destination -- every rank's gather buffer -- so the candidate exchange needs no kernel of its own. */
+MMD_API int mmd_topk_scores_shared(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
+                           int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                           size_t workspace_bytes, uint32_t* thr_local, void* const* thr_all_host, int n_thr,
+                           void* const* pair_dst_host, int n_pair_dst, int64_t pair_offset, void* stream);
+
 /* Same contraction, dense output scores f32 [Q, ld_scores] (small shapes: pairwise similarity,
  * tests, custom post-processing). */
 MMD_API int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,

@@ -36,6 +36,14 @@ __host__ __device__ __forceinline__ float key_score(uint64_t k) {
 }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~static_cast<uint32_t>(k); }
 
+// Packed copies of a result list: {score bits, row} pairs stored to up to 16 buffers (every rank's gather buffer of a
+// row-sharded corpus, peer-mapped) at pair offset `offset` + position.
+struct PairOut {
+  int2* dst[16];
+  int n;
+  int64_t offset;
+};
+
 // ---------------------------------------------------------------- host-side error plumbing
 void set_last_error(const char* fmt, ...);
 void count_launch(int n = 1);

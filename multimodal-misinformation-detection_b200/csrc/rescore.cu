@@ -6,9 +6,9 @@
 // src/evidence/im2im_retrieval.py:38-42) -- and re-ranks.  Returned scores therefore agree with the fp32
 // reference to rounding, and the order inside the returned list is the fp32 order.
 //
-// One 128-thread block per query: warps stride over candidates, each computing one D-long dot product
-// with 128-bit gathered loads (HBM/L2-bound gather: Q * k_in * D * sizeof(src) bytes), then a rank-by-
-// counting pass orders the <= 1024 candidates.
+// Up to 32 candidates: one warp per query (rescore_warp_kernel).  Longer lists: one 128-thread block per query, warps
+// stride over candidates, each computing one D-long dot product with 128-bit gathered loads (HBM/L2-bound gather:
+// Q * k_in * D * sizeof(src) bytes), then a rank-by-counting pass orders the <= 1024 candidates.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -128,6 +128,47 @@ rescore_kernel(const TQ* __restrict__ q_src, int64_t q_stride, const float* __re
   for (int i = k_in + threadIdx.x; i < k_out; i += 128) emit(out_s, out_i, pairs, q * k_out + i, __int_as_float(0xff800000), -1);
 }
 
+// Lists of at most 32 candidates (every default configuration: K' = K + 8): ONE WARP per query, four queries per block,
+// no shared memory and no block barrier.  The 32 candidate rows arrive with one coalesced load; the rows that live in this
+// shard (all of them for an unsharded corpus, K'/world on average after a global candidate merge) are re-scored one after
+// the other, each lane keeps the key of "its" candidate, and the ranks come from a shuffle sweep.
+template <typename TQ, typename TC>
+__global__ void __launch_bounds__(128)
+rescore_warp_kernel(const TQ* __restrict__ q_src, int64_t q_stride, const float* __restrict__ q_inv,
+                    const TC* __restrict__ c_src, int64_t c_stride, const float* __restrict__ c_inv, int64_t Q, int64_t N,
+                    int dim, const int32_t* __restrict__ cand_idx, int k_in, int64_t idx_offset, int k_out,
+                    float* __restrict__ out_s, int32_t* __restrict__ out_i, PairDst pairs, bool vec_ok) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const TQ* qrow = q_src + q * q_stride;
+  const float qi = q_inv != nullptr ? q_inv[q] : 1.0f;
+  const int32_t gi = lane < k_in ? cand_idx[q * k_in + lane] : -1;
+  const int64_t row = static_cast<int64_t>(gi) - idx_offset;
+  uint32_t m = __ballot_sync(0xffffffffu, gi >= 0 && row >= 0 && row < N);
+  uint64_t key = 0ull;
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    const int32_t gb = __shfl_sync(0xffffffffu, gi, b);
+    const int64_t rb = static_cast<int64_t>(gb) - idx_offset;
+    const float d = warp_dot<TQ, TC>(qrow, c_src + rb * c_stride, dim, lane, vec_ok);
+    const float ci = c_inv != nullptr ? c_inv[rb] : 1.0f;
+    if (lane == b) key = make_key(d * qi * ci, static_cast<uint32_t>(gb));
+  }
+  int rank = 0;
+  for (int t = 0; t < k_in; ++t) {
+    const uint64_t o = __shfl_sync(0xffffffffu, key, t);
+    rank += (o > key) || (o == key && t < lane);
+  }
+  if (lane < k_in && rank < k_out) {
+    const float sc = key == 0ull ? __int_as_float(0xff800000) : key_score(key);
+    const int32_t ix = key == 0ull ? -1 : static_cast<int32_t>(key_row(key));
+    emit(out_s, out_i, pairs, q * k_out + rank, sc, ix);
+  }
+  for (int i = k_in + lane; i < k_out; i += 32) emit(out_s, out_i, pairs, q * k_out + i, __int_as_float(0xff800000), -1);
+}
+
 template <typename TQ, typename TC>
 int launch(const void* q_src, int64_t q_stride, const float* q_inv, const void* c_src, int64_t c_stride,
            const float* c_inv, int64_t Q, int64_t N, int dim, const int32_t* cand_idx, int k_in, int64_t idx_offset,
@@ -135,9 +176,15 @@ int launch(const void* q_src, int64_t q_stride, const float* q_inv, const void* 
   const bool vec_ok = dim % 8 == 0 && reinterpret_cast<uintptr_t>(q_src) % 16 == 0 &&
                       reinterpret_cast<uintptr_t>(c_src) % 16 == 0 && (q_stride * sizeof(TQ)) % 16 == 0 &&
                       (c_stride * sizeof(TC)) % 16 == 0;
-  rescore_kernel<TQ, TC><<<static_cast<unsigned>(Q), 128, 0, stream>>>(
-      static_cast<const TQ*>(q_src), q_stride, q_inv, static_cast<const TC*>(c_src), c_stride, c_inv, N, dim, cand_idx,
-      k_in, idx_offset, k_out, out_s, out_i, pairs, vec_ok);
+  if (k_in <= 32) {
+    rescore_warp_kernel<TQ, TC><<<static_cast<unsigned>((Q + 3) / 4), 128, 0, stream>>>(
+        static_cast<const TQ*>(q_src), q_stride, q_inv, static_cast<const TC*>(c_src), c_stride, c_inv, Q, N, dim, cand_idx,
+        k_in, idx_offset, k_out, out_s, out_i, pairs, vec_ok);
+  } else {
+    rescore_kernel<TQ, TC><<<static_cast<unsigned>(Q), 128, 0, stream>>>(
+        static_cast<const TQ*>(q_src), q_stride, q_inv, static_cast<const TC*>(c_src), c_stride, c_inv, N, dim, cand_idx,
+        k_in, idx_offset, k_out, out_s, out_i, pairs, vec_ok);
+  }
   count_launch();
   MMD_CUDA_OK(cudaGetLastError());
   return MMD_OK;

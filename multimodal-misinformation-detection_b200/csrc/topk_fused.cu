@@ -33,7 +33,8 @@
 namespace mmd {
 
 int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
-                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream,
+                       const PairOut* po = nullptr);
 
 namespace {
 
@@ -61,6 +62,8 @@ struct FusedParams {
   int stages;
   uint64_t* partial;     // [Q][S][kprime] keys
   uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
+  uint32_t* thr_peer[8]; // row-sharded corpus: the same array on EVERY rank (peer-mapped, own one included); a bound
+  int n_thr_peers;       //   learnt on one shard prunes all of them.  0 = publish to thr_global only.
   float* dense;          // dense mode: [Q][ldd] scores
   int64_t ldd;
   float out_scale;       // dense mode: multiplier applied to the accumulators
@@ -274,8 +277,15 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
 // value is the next float BELOW a row's current K-th best, so that "score > bound" still admits a score equal
 // to that K-th best (the (score desc, row asc) tie rule is decided later, by the sorts).  Any K-th best of a
 // subset of the corpus is a valid lower bound for the K-th best of the whole corpus.
-__device__ __forceinline__ void publish_threshold(uint32_t* thr_global, int64_t qrow, float thr) {
-  atomicMax(thr_global + qrow, float_to_ordered(thr) - 1u);
+// With a row-sharded corpus the K-th best of one GPU's shard is equally a lower bound for the global K-th best, so a
+// publication goes to the threshold array of every rank (system-scope atomics over NVLink on peer-mapped memory).
+__device__ __forceinline__ void publish_threshold(const FusedParams& p, int64_t qrow, float thr) {
+  const uint32_t v = float_to_ordered(thr) - 1u;
+  if (p.n_thr_peers == 0) {
+    atomicMax(p.thr_global + qrow, v);
+  } else {
+    for (int i = 0; i < p.n_thr_peers; ++i) atomicMax_system(p.thr_peer[i] + qrow, v);
+  }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -467,7 +477,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int i = 1; i < 32; ++i) kth = (i == p.kprime - 1) ? gmx[i] : kth;
             if (valid && thr == kNegInf && kth > kNegInf) {
-              publish_threshold(p.thr_global, qrow, kth);
+              publish_threshold(p, qrow, kth);
               thr = ordered_to_float(float_to_ordered(kth) - 1u);     // admit scores equal to the bound
             }
           }
@@ -538,7 +548,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
                 cnt = st.cnt;
                 thr = st.thr;
-                if (thr != before) publish_threshold(p.thr_global, qrow, thr);
+                if (thr != before) publish_threshold(p, qrow, thr);
               }
               // branch-free appends: raw entry {~column, score bits} stored under a predicate
               const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
@@ -570,7 +580,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                                                     static_cast<int64_t>(p.n_strips) * p.kprime);
         cnt = st.cnt;
         thr = st.thr;
-        if (valid && thr != before) publish_threshold(p.thr_global, qrow, thr);
+        if (valid && thr != before) publish_threshold(p, qrow, thr);
       }
     }
   }
@@ -869,10 +879,11 @@ extern "C" size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op
   return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + static_cast<size_t>(Q) * sizeof(uint32_t) + 256;
 }
 
-extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
-                               int k, int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-  using namespace mmd;
+namespace mmd {
+namespace {
+int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
+                     int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                     uint32_t* thr_local, void* const* thr_all_host, int n_thr, const PairOut* po, void* stream) {
   MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k > 0, "mmd_topk_scores: Q=%lld N=%lld dim=%d k=%d", (long long)Q,
               (long long)N, dim, k);
   MMD_REQUIRE(N < (1ll << 31) && Q < (1ll << 31), "mmd_topk_scores: Q and N must be < 2^31");
@@ -886,7 +897,7 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   MMD_REQUIRE(cap != 0, "mmd_topk_scores: k=%d exceeds the fused selection limit %d", k, mmd_topk_max_k());
   if (N == 0) {
     // empty corpus: every slot is (-inf, -1)
-    return merge_partial_keys(nullptr, 0, Q, k, k, 1.0f, idx_offset, out_scores, out_idx, st);
+    return merge_partial_keys(nullptr, 0, Q, k, k, 1.0f, idx_offset, out_scores, out_idx, st, po);
   }
   MMD_REQUIRE(q_prep != nullptr && c_prep != nullptr, "mmd_topk_scores: null operand");
   MMD_REQUIRE(reinterpret_cast<uintptr_t>(q_prep) % 16 == 0 && reinterpret_cast<uintptr_t>(c_prep) % 16 == 0,
@@ -918,8 +929,16 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   p.kprime = k;
   p.stages = stages_for(cap, cta);
   p.partial = static_cast<uint64_t*>(workspace);
-  p.thr_global = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + keys_bytes);
-  MMD_CUDA_OK(cudaMemsetAsync(p.thr_global, 0, static_cast<size_t>(Q) * sizeof(uint32_t), st));
+  if (thr_local == nullptr) {
+    p.thr_global = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + keys_bytes);
+    MMD_CUDA_OK(cudaMemsetAsync(p.thr_global, 0, static_cast<size_t>(Q) * sizeof(uint32_t), st));
+    p.n_thr_peers = 0;
+  } else {
+    // caller-owned threshold arrays shared by all ranks of a row-sharded corpus (zeroed by the caller before the step)
+    p.thr_global = thr_local;
+    p.n_thr_peers = n_thr;
+    for (int i = 0; i < n_thr; ++i) p.thr_peer[i] = static_cast<uint32_t*>(thr_all_host[i]);
+  }
   p.dense = nullptr; p.ldd = 0; p.out_scale = 1.0f;
   p.status = device_status_word();
   p.stats = nullptr;
@@ -948,7 +967,40 @@ extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dt
   if (rc != MMD_OK) return rc;
 
   const float scale = f8 ? (1.0f / 65536.0f) : 1.0f;
-  return merge_partial_keys(p.partial, sch.S, Q, k, k, scale, idx_offset, out_scores, out_idx, st);
+  return merge_partial_keys(p.partial, sch.S, Q, k, k, scale, idx_offset, out_scores, out_idx, st, po);
+}
+}  // namespace
+}  // namespace mmd
+
+extern "C" int mmd_topk_scores(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
+                               int k, int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  return mmd::topk_scores_impl(q_prep, c_prep, op_dtype, Q, N, dim, k, idx_offset, out_scores, out_idx, workspace,
+                               workspace_bytes, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int mmd_topk_scores_shared(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,
+                                      int k, int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                                      size_t workspace_bytes, uint32_t* thr_local, void* const* thr_all_host, int n_thr,
+                                      void* const* pair_dst_host, int n_pair_dst, int64_t pair_offset, void* stream) {
+  using namespace mmd;
+  MMD_REQUIRE(n_pair_dst >= 0 && n_pair_dst <= 16 && (n_pair_dst == 0 || pair_dst_host != nullptr) && pair_offset >= 0,
+              "mmd_topk_scores_shared: n_pair_dst=%d (0..16)", n_pair_dst);
+  PairOut po{};
+  po.n = n_pair_dst;
+  po.offset = pair_offset;
+  for (int i = 0; i < n_pair_dst; ++i) {
+    MMD_REQUIRE(pair_dst_host[i] != nullptr && reinterpret_cast<uintptr_t>(pair_dst_host[i]) % 8 == 0,
+                "mmd_topk_scores_shared: pair destination %d is null or not 8-byte aligned", i);
+    po.dst[i] = static_cast<int2*>(pair_dst_host[i]);
+  }
+  MMD_REQUIRE(thr_local != nullptr && thr_all_host != nullptr && n_thr >= 1 && n_thr <= 8,
+              "mmd_topk_scores_shared: thr_local / thr_all_host null or n_thr=%d not in 1..8", n_thr);
+  for (int i = 0; i < n_thr; ++i)
+    MMD_REQUIRE(thr_all_host[i] != nullptr && reinterpret_cast<uintptr_t>(thr_all_host[i]) % 4 == 0,
+                "mmd_topk_scores_shared: threshold array %d is null or misaligned", i);
+  return topk_scores_impl(q_prep, c_prep, op_dtype, Q, N, dim, k, idx_offset, out_scores, out_idx, workspace,
+                          workspace_bytes, thr_local, thr_all_host, n_thr, n_pair_dst > 0 ? &po : nullptr, stream);
 }
 
 extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,

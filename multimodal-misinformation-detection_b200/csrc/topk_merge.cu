@@ -20,6 +20,7 @@ namespace {
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct MergeSrc {
+  PairOut po;             // optional packed copies of the result (see PairOut)
   const uint64_t* keys;   // [Q][parts * k_in]                    (keys != nullptr)
   const int2* pairs;      // [parts][Q][k_in] {score bits, row}    (keys == nullptr, pairs != nullptr)
   const float* scores;    // [parts][Q][k_in]                      (otherwise)
@@ -43,14 +44,14 @@ __device__ __forceinline__ uint64_t load_candidate(const MergeSrc& s, int64_t q,
 }
 
 __device__ __forceinline__ void store_result(uint64_t key, float scale, int64_t idx_offset, float* out_s,
-                                             int32_t* out_i) {
-  if (key == 0ull) {
-    *out_s = __int_as_float(0xff800000);
-    *out_i = -1;
-  } else {
-    *out_s = key_score(key) * scale;
-    *out_i = static_cast<int32_t>(static_cast<int64_t>(key_row(key)) + idx_offset);
-  }
+                                             int32_t* out_i, const PairOut& po = PairOut{}, int64_t pos = 0) {
+  const float sc = key == 0ull ? __int_as_float(0xff800000) : key_score(key) * scale;
+  const int32_t ix = key == 0ull ? -1 : static_cast<int32_t>(static_cast<int64_t>(key_row(key)) + idx_offset);
+  *out_s = sc;
+  *out_i = ix;
+  // row-sharded corpora: the merged list also goes, packed, straight into every rank's gather buffer
+  const int2 v = make_int2(__float_as_int(sc), ix);
+  for (int d = 0; d < po.n; ++d) po.dst[d][po.offset + pos] = v;
 }
 
 template <int E>
@@ -173,9 +174,10 @@ merge_stream_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, fl
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int i = e * 32 + lane;
-    if (i < k_out) store_result(best[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+    if (i < k_out) store_result(best[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
   }
-  for (int i = L + lane; i < k_out; i += 32) store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+  for (int i = L + lane; i < k_out; i += 32)
+    store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
 }
 
 template <int L>
@@ -199,7 +201,7 @@ merge_block_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, flo
     }
   }
   for (int i = threadIdx.x; i < k_out; i += 256)
-    store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
+    store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
 }
 
 template <bool kSortedParts>
@@ -228,8 +230,9 @@ int launch_merge(const MergeSrc& src, int k_out, float scale, int64_t idx_offset
 }  // namespace
 
 int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
-                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream) {
+                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream, const PairOut* po) {
   MergeSrc src{};
+  if (po != nullptr) src.po = *po;
   src.keys = partial;
   src.pairs = nullptr;
   src.scores = nullptr;

@@ -140,8 +140,13 @@ def overfetch_for(k: int, n: int) -> int:
     return max(1, min(n, max(k, min(k + max(8, k // 2), 104)), max_k()))
 
 
-def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """K2+K3 (+K3b): fused contraction + top-k over prepared operands -> (scores f32 [Q,k], idx i32 [Q,k])."""
+def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, k: int,
+                  shared_thr: Optional[Tuple[int, Sequence[int]]] = None,
+                  pair_dst: Optional[Tuple[Sequence[int], int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2+K3 (+K3b): fused contraction + top-k over prepared operands -> (scores f32 [Q,k], idx i32 [Q,k]).
+    shared_thr = (device pointer of this rank's threshold array, device pointers of every rank's array): row-sharded
+    corpora share their pruning thresholds across GPUs (mmd_topk_scores_shared); pair_dst = (device pointers, pair offset):
+    the strip merge also stores the packed list into those buffers (every rank's gather buffer)."""
     lib = _lib.load()
     dev = corpus.device
     scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
@@ -152,8 +157,17 @@ def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, 
     ws_bytes = int(lib.mmd_topk_workspace_bytes(n_queries, max(corpus.n, 1), corpus.dim, op, k))
     ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.mmd_topk_scores(_ptr(q_rows), _ptr(corpus.rows), op, n_queries, corpus.n, corpus.dim, k, corpus.idx_offset,
-                                 _ptr(scores), _ptr(idx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+        if shared_thr is None:
+            rc = lib.mmd_topk_scores(_ptr(q_rows), _ptr(corpus.rows), op, n_queries, corpus.n, corpus.dim, k, corpus.idx_offset,
+                                     _ptr(scores), _ptr(idx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+        else:
+            local, everyone = shared_thr
+            arr = (C.c_void_p * len(everyone))(*[C.c_void_p(int(p)) for p in everyone])
+            dsts, off = pair_dst if pair_dst is not None else ((), 0)
+            darr = (C.c_void_p * max(len(dsts), 1))(*[C.c_void_p(int(p)) for p in dsts])
+            rc = lib.mmd_topk_scores_shared(_ptr(q_rows), _ptr(corpus.rows), op, n_queries, corpus.n, corpus.dim, k, corpus.idx_offset,
+                                            _ptr(scores), _ptr(idx), _ptr(ws), ws_bytes, C.c_void_p(int(local)), arr, len(everyone),
+                                            darr, len(dsts), int(off), _stream_ptr(dev))
     _lib.check(rc, "mmd_topk_scores")
     return scores, idx
 
@@ -196,7 +210,8 @@ def rescore_pairs(q: torch.Tensor, q_inv: Optional[torch.Tensor], corpus: Prepar
     _lib.check(rc, "mmd_rescore_pairs")
 
 
-def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int] = None):
+def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int] = None,
+                    shared_thr: Optional[Tuple[int, Sequence[int]]] = None, pair_dst: Optional[Tuple[Sequence[int], int]] = None):
     """First half of the default path: K1 on the queries + fused tensor-core top-K' (K' = over-fetched k).
     Returns (q rows on the device, q inv_norm or None, raw scores f32 [Q,K'], candidate rows i32 [Q,K'])."""
     q = _as_rows(queries, pc.device)
@@ -205,7 +220,8 @@ def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int
     k_eff = min(k, pc.n)
     kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
     q_rows, q_inv = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
-    scores, idx = topk_prepared(q_rows, q.shape[0], pc, max(kprime, 1))
+    scores, idx = topk_prepared(q_rows, q.shape[0], pc, max(kprime, 1), shared_thr=shared_thr if pc.n > 0 else None,
+                                pair_dst=pair_dst if (pc.n > 0 and shared_thr is not None) else None)
     return q, (q_inv if pc.metric == "cos" else None), scores, idx
 
 

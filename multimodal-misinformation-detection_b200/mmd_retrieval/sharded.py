@@ -56,13 +56,25 @@ class _PeerExchange:
     after every peer has finished its own stores of step i, which in stream order come after that peer's last read of
     step i-1 -- and the buffer written in step i+1 was last read in step i-1."""
 
-    def __init__(self, group, world: int, cap_pairs: int, device: torch.device):
+    def __init__(self, group, world: int, cap_pairs: int, q_cap: int, device: torch.device):
         import torch.distributed._symmetric_memory as symm_mem
-        self.world, self.cap = world, cap_pairs
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.cap, self.q_cap = world, cap_pairs, q_cap
         self.buf = symm_mem.empty((2, world, cap_pairs, 2), dtype=torch.int32, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # per-query pruning thresholds shared by all ranks (one array per step parity), see mmd_topk_scores_shared
+        self.thr = symm_mem.empty((2, q_cap), dtype=torch.int32, device=device)
+        self.thr_hdl = symm_mem.rendezvous(self.thr, grp)
+        self.thr_ptrs = [int(p) for p in self.thr_hdl.buffer_ptrs]
+        self.thr.zero_()
         self.step = 0
+        self.hdl.barrier(channel=0)            # every rank's threshold arrays are zero before anyone publishes
+
+    def thr_slot(self, parity: int):
+        """(this rank's threshold array of the given parity, every rank's) as device pointers."""
+        off = parity * self.q_cap * 4
+        return self.thr.data_ptr() + off, [p + off for p in self.thr_ptrs]
 
     def slot(self, parity: Optional[int] = None):
         """(peer base pointers of this step's buffer, local view [world, cap, 2] of it)."""
@@ -81,7 +93,7 @@ class ShardedCorpus:
     """This rank's shard of a row-sharded corpus plus the collective that merges local top-K lists."""
 
     def __init__(self, local_rows, n_total: int, start: int, group=None, dtype: str = "bf16", metric: str = "cos",
-                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: str = "global",
+                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: str = "global", share_thresholds: bool = True,
                  local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, prepare: Optional[Callable] = None,
                  _shard=None):
         self.group = group
@@ -95,6 +107,7 @@ class ShardedCorpus:
         if rescore not in ("global", "local"):
             raise ValueError("rescore must be 'global' or 'local'")
         self.rescore = rescore
+        self.share_thresholds = share_thresholds
         self._exchange_req = exchange
         self.exchange = "nccl"            # what is actually in use; "peer" once symmetric memory is up on every rank
         self._peer: Optional[_PeerExchange] = None
@@ -163,7 +176,7 @@ class ShardedCorpus:
         kp_glob = ops.overfetch_for(min(k, self._max_local), self._max_local)
         two_phase = self.rescore == "global"
         cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
-        peer = self._peer_for(cap, dev)
+        peer = self._peer_for(cap, n_queries, dev)
         return self._search(q, k, k_glob, kp_glob, peer, two_phase, peer.step % 2 if peer is not None else 0, advance=True)
 
     def upload_queries(self, queries, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -201,9 +214,16 @@ class ShardedCorpus:
         shard, dev, world, rank = self.shard, self.shard.device, self.world, self.rank
         n_queries = q.shape[0]
         # (an empty shard goes through the same calls: every candidate is (-inf, -1))
-        qd, q_inv, raw_s, cand = ops.topk_candidates(q, shard, k, overfetch=kp_glob)
+        # peer memory + global stage order: the pruning thresholds are shared across the GPUs as well
+        share_thr = peer is not None and two_phase and self.share_thresholds
         if peer is not None:
             ptrs, local = peer.slot(parity)                        # local: [world, cap, 2]
+        # ... and when this shard can fill the common list width, the strip merge stores the raw candidate list straight
+        # into every rank's gather buffer (no scatter kernel)
+        fused_scatter = share_thr and shard.n >= kp_glob
+        qd, q_inv, raw_s, cand = ops.topk_candidates(q, shard, k, overfetch=kp_glob,
+                                                     shared_thr=peer.thr_slot(parity) if share_thr else None,
+                                                     pair_dst=(ptrs, rank * peer.cap) if fused_scatter else None)
 
         def exchange(fill, width, region_off):
             """fill(dst_ptrs, pair_offset) stores this rank's [Q, width] list; returns the gathered [world] lists as
@@ -235,7 +255,12 @@ class ShardedCorpus:
             if kp < kp_glob:                                       # a small shard: pad its raw list to the common width
                 raw_s = torch.cat([raw_s, raw_s.new_full((n_queries, kp_glob - kp), float("-inf"))], dim=1).contiguous()
                 cand = torch.cat([cand, cand.new_full((n_queries, kp_glob - kp), -1)], dim=1).contiguous()
-            g1 = exchange(lambda d, off: ops.scatter_pairs(raw_s, cand, d, off), kp_glob, 0)
+            g1 = exchange((lambda d, off: None) if fused_scatter else (lambda d, off: ops.scatter_pairs(raw_s, cand, d, off)),
+                          kp_glob, 0)
+            if share_thr:
+                # between the step's two barriers: every rank is past this step's contraction, nobody can have begun the
+                # next one -- the other parity's thresholds (used by the next step) are cleared here
+                peer.thr[1 - parity, :n_queries].zero_()
             kc = min(world * kp_glob, ops.overfetch_for(k_glob, self.n_total))
             _, cand_glob = merged(g1, kp_glob, kc)                 # the global K' candidates, identical on every rank
             g2 = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand_glob, k_glob, d, dst_offset_pairs=off),
@@ -254,17 +279,17 @@ class ShardedCorpus:
         until the next replay of the same parity."""
         return GraphedSearch(self, queries, k)
 
-    def _peer_for(self, n_pairs: int, dev: torch.device) -> Optional[_PeerExchange]:
+    def _peer_for(self, n_pairs: int, n_queries: int, dev: torch.device) -> Optional[_PeerExchange]:
         """Symmetric gather buffers big enough for n_pairs per rank, or None (-> NCCL).  Collective: every rank
         calls it with the same n_pairs and all of them agree on the outcome."""
         if self._exchange_req == "nccl" or self._peer_failed:
             return None
-        if self._peer is not None and self._peer.cap >= n_pairs:
+        if self._peer is not None and self._peer.cap >= n_pairs and self._peer.q_cap >= n_queries:
             return self._peer
         ok = 1
         peer = None
         try:
-            peer = _PeerExchange(self.group, self.world, n_pairs, dev)
+            peer = _PeerExchange(self.group, self.world, n_pairs, n_queries, dev)
         except Exception as e:  # noqa: BLE001
             ok = 0
             self._peer_error = repr(e)
@@ -325,7 +350,7 @@ class GraphedSearch:
             cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
             sc.topk(self.q_static, k)                              # warm-up: lazy initialisation (attributes, symmetric memory)
             if sc.exchange == "peer":
-                self.peer = _PeerExchange(sc.group, sc.world, cap, dev)      # this object's own double buffer
+                self.peer = _PeerExchange(sc.group, sc.world, cap, n_queries, dev)      # this object's own double buffer
         else:
             ops.topk(self.q_static, sc.shard, k)
         torch.cuda.synchronize(dev)

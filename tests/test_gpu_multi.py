@@ -46,7 +46,7 @@ def _worker(rank, world, port, out):
             s2, i2 = sc.topk(queries, 10)
             assert torch.equal(i2, i) and torch.equal(s2, s)
         # both exchange implementations and both stage orders give the same lists
-        for kw in ({"exchange": "nccl"}, {"rescore": "local"}, {"exchange": "nccl", "rescore": "local"}):
+        for kw in ({"exchange": "nccl"}, {"rescore": "local"}, {"exchange": "nccl", "rescore": "local"}, {"share_thresholds": False}):
             other = m.ShardedCorpus.from_full(corpus.cuda(), **kw)
             s3, i3 = other.topk(queries.cuda(), 10)
             assert other.exchange == kw.get("exchange", sc.exchange)
