@@ -23,7 +23,7 @@ if [ -z "$QUICK" ]; then
   echo "ref rc=$?"
   # the other BASELINE configs (c4 / c5: one GPU's 1/8 share of the 8-GPU configuration)
   for wl in c1 c2 c4 c5; do
-    python bench.py --workload $wl --steps 10 --warmup 3 --no-extra > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
+    python bench.py --workload $wl --steps 30 --warmup 5 --no-extra > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
     echo "bench $wl rc=$?"
   done
   python tools/gpu_diag.py perf2 k1perf > "$OUT/diag_perf.log" 2>&1
