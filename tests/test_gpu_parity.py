@@ -340,6 +340,46 @@ def test_packed_pairs_exchange_layout(m):
     assert bool(torch.isinf(one[0, :, 4:, 0].view(torch.float32)).all())
 
 
+def test_global_rescore_flow_with_shared_thresholds_emulated_on_one_gpu(m):
+    """The production multi-GPU step, stage by stage, with three 'ranks' emulated on one device: per-shard tensor-core
+    pass whose pruning thresholds are SHARED between the shards (mmd_topk_scores_shared: a bound learnt on one shard
+    prunes the others) and whose strip merge stores the raw candidates straight into every rank's gather buffer ->
+    strided merge of the raw lists -> each shard re-scores only the global candidates it owns into the second region ->
+    final merge.  Must equal the unsharded result bit for bit."""
+    from mmd_retrieval import ops, _lib
+    from mmd_retrieval.sharded import shard_bounds
+    q, c = _data("text", 300, 768, 64), _data("text", 20011, 768, 65)
+    c[20010] = c[7]                                                # equal scores on different shards
+    q[0] = c[7] * 1.5
+    k, world = 10, 3
+    want_s, want_i = m.topk(q.cuda(), c.cuda(), k)
+    n_q, kp = q.shape[0], ops.overfetch_for(k, 6671)
+    cap = n_q * (kp + k)
+    gather = [torch.zeros((world, cap, 2), dtype=torch.int32, device="cuda") for _ in range(world)]     # one buffer per "rank"
+    thr = [torch.zeros((n_q,), dtype=torch.int32, device="cuda") for _ in range(world)]
+    shards, qd, q_inv = [], None, None
+    for r in range(world):                                          # stage 1 on every rank (sequentially here)
+        lo, hi = shard_bounds(c.shape[0], world, r)
+        pc = m.prepare_corpus(c[lo:hi].cuda(), idx_offset=lo)
+        shards.append(pc)
+        qd, q_inv, raw_s, cand = ops.topk_candidates(q.cuda(), pc, k, overfetch=kp,
+                                                     shared_thr=(thr[r].data_ptr(), [t.data_ptr() for t in thr]),
+                                                     pair_dst=([g.data_ptr() for g in gather], r * cap))
+        assert cand.shape[1] == kp
+        # every bound this shard learnt was published to EVERY rank's threshold array
+        assert int((thr[0] != 0).sum()) == n_q and all(torch.equal(t, thr[0]) for t in thr[1:])
+        # the raw list arrived, packed, in slot r of every rank's buffer
+        assert torch.equal(gather[0][r, :n_q * kp, 1].view(n_q, kp), cand) and torch.equal(gather[0], gather[world - 1])
+    for g in gather[1:]:
+        assert torch.equal(g, gather[0])
+    _, cand_glob = ops.merge_pairs(gather[0], kp, n_queries=n_q, k_in=kp, parts_sorted=True)
+    for r in range(world):                                          # stage 2: every rank re-scores what it owns
+        ops.rescore_pairs(qd, q_inv, shards[r], cand_glob, k, [g.data_ptr() for g in gather], dst_offset_pairs=r * cap + n_q * kp)
+    s, i = ops.merge_pairs_at(gather[1][:, n_q * kp:, :], cap, k, n_q, k, parts_sorted=True)
+    assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
+    assert i[0, :2].tolist() == [7, 20010]
+
+
 # ------------------------------------------------------------------------------------------ joint image+text fusion
 @pytest.mark.parametrize("op,dims,weights", [("bf16", (512, 512), (0.5, 0.5)), ("bf16", (768, 2048), (0.7, 0.3)),
                                              ("fp16", (100, 36), (0.25, 0.75)), ("bf16", (64, 64, 32), (0.2, 0.3, 0.5))])
