@@ -60,6 +60,8 @@ struct FusedParams {
   int n_units;           // n_m * S
   int kprime;            // list length kept per (query, strip)
   int stages;
+  int a_rows;            // query rows staged per CTA and K block: 128, or the 32-row groups a batch of < 128 queries fills
+  int key_warps;         // epilogue warps (lane quarters 0 .. key_warps-1) that own candidate buffers: a_rows / 32
   uint64_t* partial;     // [Q][S][kprime] keys
   uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
   uint32_t* thr_peer[8]; // row-sharded corpus: the same array on EVERY rank (peer-mapped, own one included); a bound
@@ -87,11 +89,14 @@ struct SmemLayout {
   uint32_t tmem_ptr_off;
   uint32_t total;        // including 1024 B of alignment slack
 };
-__host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta) {
+// a_rows / key_warps: see FusedParams.  A small batch (the reference's one-claim-per-call pattern) is an HBM-bound corpus
+// stream; staging only the query rows that exist (4 KB instead of 16 KB per stage for <= 32 queries) and only their
+// candidate buffers (16 KB instead of 64 KB) buys two more TMA stages, i.e. 160 KB instead of 96 KB of corpus in flight per SM.
+__host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta, int a_rows = kTileM, int key_warps = 4) {
   SmemLayout l;
   l.stage_off = 0;
-  l.keys_off = stages * stage_bytes(cta);
-  l.bars_off = l.keys_off + cap * 32 * 4 * 8;
+  l.keys_off = stages * (a_rows * kBlockKBytes + b_bytes(cta));
+  l.bars_off = l.keys_off + cap * 32 * key_warps * 8;
   l.tmem_ptr_off = l.bars_off + (2 * kMaxStages + 4) * 8;
   l.total = l.tmem_ptr_off + 16 + 1024;
   return l;
@@ -298,13 +303,14 @@ template <int CAP, bool kF8, bool kDense, int kCta>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                         const FusedParams p, const uint32_t idesc) {
-  constexpr int kStageBytes = stage_bytes(kCta);
+  const int a_bytes = p.a_rows * kBlockKBytes;          // B starts right after the staged query rows (1 KB multiple)
+  const int stage_sz = a_bytes + b_bytes(kCta);
   constexpr int kUnitRows = kTileM * kCta;        // queries per unit (per CTA pair)
   constexpr int kBRows = kTileN / kCta;           // corpus rows this CTA stages per tile
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024-byte alignment.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta);
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta, p.a_rows, p.key_warps);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
@@ -357,17 +363,17 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const int c_row = t * kTileN + static_cast<int>(cta_rank) * kBRows;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, p.status, 1);
-            uint8_t* sa = smem + L.stage_off + stage * kStageBytes;
+            uint8_t* sa = smem + L.stage_off + stage * stage_sz;
             const int kelem = kb * (kF8 ? kBlockKBytes : kBlockKBytes / 2);
             if constexpr (kCta == 1) {
-              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              mbar_arrive_expect_tx(&full_bar[stage], stage_sz);
               tma_load_2d(sa, &tmap_q, &full_bar[stage], kelem, q_row, kEvictLast);
-              tma_load_2d(sa + kABytes, &tmap_c, &full_bar[stage], kelem, c_row, kEvictNormal);
+              tma_load_2d(sa + a_bytes, &tmap_c, &full_bar[stage], kelem, c_row, kEvictNormal);
             } else {
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_sz);
               const uint32_t bar = full_addr0 + stage * 8;
               tma_load_2d_2sm(sa, &tmap_q, bar, kelem, q_row, kEvictLast);
-              tma_load_2d_2sm(sa + kABytes, &tmap_c, bar, kelem, c_row, kEvictNormal);
+              tma_load_2d_2sm(sa + a_bytes, &tmap_c, bar, kelem, c_row, kEvictNormal);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -394,9 +400,11 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&full_bar[stage], phase, p.status, 3);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + L.stage_off + stage * kStageBytes);
+            // (with a_rows = 32 the 128-row A descriptor also covers what follows the staged rows: those accumulator
+            //  lanes belong to query rows >= Q, which no epilogue thread ever reads a candidate from)
+            const uint32_t sa = smem_u32(smem + L.stage_off + stage * stage_sz);
             const uint64_t adesc = make_smem_desc_sw128(sa);
-            const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes);
+            const uint64_t bdesc = make_smem_desc_sw128(sa + a_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockKBytes / 32; ++k) {
               // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -417,7 +425,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(warp - 2) * (CAP * 32);
+    // candidate buffers are indexed by the lane quarter (= 32-row group of the tile); with key_warps = 1 only quarter 0
+    // (query rows 0..31) owns one -- the other warps' rows are all beyond Q and never touch theirs
+    uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(quarter) * (CAP * 32);
     const uint32_t row_addr = smem_u32(wkeys) + static_cast<uint32_t>(lane) * 8u;   // slot 0 of this thread's own row
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
@@ -743,7 +753,7 @@ constexpr size_t kMaxProfiled = 512;
 template <int CAP, bool kF8, bool kDense, int kCta>
 int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams& p, uint32_t idesc, int grid,
                  cudaStream_t stream) {
-  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta);
+  const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta, p.a_rows, p.key_warps);
   auto kern = fused_score_topk_kernel<CAP, kF8, kDense, kCta>;
   static bool attr_set = false;   // one per template instantiation
   if (!attr_set) {
@@ -803,12 +813,22 @@ int launch_any(bool f8, int cta, const CUtensorMap& tq, const CUtensorMap& tc, c
             : launch_fused<CAP, false, kDense, 1>(tq, tc, p, idesc, grid, stream);
 }
 
-int stages_for(int cap, int cta) {
+int stages_for(int cap, int cta, int a_rows = kTileM, int key_warps = 4) {
   static const int forced = [] { const char* e = getenv("MMD_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
-  if (forced >= 2 && forced <= kMaxStages && smem_layout(forced, cap, cta).total <= static_cast<uint32_t>(kMaxSmem)) return forced;
+  if (forced >= 2 && forced <= kMaxStages &&
+      smem_layout(forced, cap, cta, a_rows, key_warps).total <= static_cast<uint32_t>(kMaxSmem)) return forced;
   for (int st = kMaxStages; st >= 2; --st)
-    if (smem_layout(st, cap, cta).total <= static_cast<uint32_t>(kMaxSmem)) return st;
+    if (smem_layout(st, cap, cta, a_rows, key_warps).total <= static_cast<uint32_t>(kMaxSmem)) return st;
   return 0;
+}
+
+// A batch of fewer than 128 queries (one 1-CTA tile whose upper rows do not exist) stages only the 32-row groups that
+// exist and keeps candidate buffers only for those; tuning knob MMD_SMALL_BATCH=0 switches the variant off.
+// Measured on a 1 M x 768 bf16 corpus, Q = 1: 4.5 -> 6.7 TB/s of corpus stream (0.341 -> 0.229 ms).
+int staged_query_rows(int64_t Q, int cta) {
+  static const int enabled = [] { const char* e = getenv("MMD_SMALL_BATCH"); return e ? atoi(e) : 1; }();
+  if (enabled == 0 || cta != 1 || Q >= kTileM) return kTileM;
+  return static_cast<int>(round_up(Q, 32));
 }
 
 int sm_count() {
@@ -917,7 +937,9 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   MMD_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 8 == 0, "mmd_topk_scores: workspace must be 8-byte aligned");
 
   CUtensorMap tq, tc;
-  rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, kTileM);
+  const int a_rows = staged_query_rows(Q, cta);
+  const int key_warps = a_rows / 32;
+  rc = make_rows_tensor_map(&tq, q_prep, op_dtype, Q, lay, a_rows);
   if (rc != MMD_OK) return rc;
   rc = make_rows_tensor_map(&tc, c_prep, op_dtype, N, lay, kTileN / cta);
   if (rc != MMD_OK) return rc;
@@ -927,7 +949,8 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = sch.T; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = k;
-  p.stages = stages_for(cap, cta);
+  p.a_rows = a_rows; p.key_warps = key_warps;
+  p.stages = stages_for(cap, cta, a_rows, key_warps);
   p.partial = static_cast<uint64_t*>(workspace);
   if (thr_local == nullptr) {
     p.thr_global = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + keys_bytes);
@@ -1035,6 +1058,7 @@ extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_d
   p.kblocks = static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes));
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = 1; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = 0;
+  p.a_rows = kTileM; p.key_warps = 4;
   p.stages = stages_for(0, cta);
   if (p.stages > 6) p.stages = 6;
   p.partial = nullptr;

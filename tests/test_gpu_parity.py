@@ -159,6 +159,9 @@ CASES = [
     ("text", 129, 257, 64, 7, "bf16"),          # one past every tile edge
     ("text", 127, 255, 100, 7, "bf16"),         # D not a multiple of 8
     ("text", 1, 41256, 768, 50, "bf16"),        # one query, the reference's usage pattern
+    ("text", 33, 9000, 768, 10, "bf16"),        # small batches stage only the 32-row query groups that exist (1, 2, 3 groups)
+    ("text", 64, 9000, 768, 10, "fp8"),
+    ("image", 70, 5000, 2048, 10, "bf16"),
 ]
 
 
