@@ -227,7 +227,7 @@ def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int
 
 def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None,
          rescore_exact: Optional[bool] = None, overfetch: Optional[int] = None,
-         index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
+         index_dtype: torch.dtype = torch.int64, dense_fallback: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k most similar corpus rows for every query.
 
     queries : [Q,D] (or [D]) tensor / ndarray / list, any device (moved to the corpus device).
@@ -236,6 +236,9 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
 
     rescore_exact (default: on when the corpus kept its source embeddings) over-fetches candidates with the
     tensor-core pass and recomputes their scores in fp32 from the original embeddings.
+    dense_fallback: k beyond the fused selection's limit (120) is served by the dense tensor-core contraction plus a
+    device-side stable sort of the score rows (query chunks of <= 1 GB of scores) -- off the hot path, for drop-in
+    completeness only (the reference's largest list is top_k*10 = 100, experiment_text.py:26).
     """
     if k <= 0:
         raise ValueError("k must be positive")
@@ -252,7 +255,9 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
         return (torch.empty((n_queries, 0), dtype=torch.float32, device=pc.device),
                 torch.empty((n_queries, 0), dtype=index_dtype, device=pc.device))
     if k_eff > max_k():
-        raise _lib.MmdError(f"k={k_eff} exceeds the fused top-k limit {max_k()} (use dense_scores for a full ranking)")
+        if not dense_fallback:
+            raise _lib.MmdError(f"k={k_eff} exceeds the fused top-k limit {max_k()} (pass dense_fallback=True for a ranked dense pass)")
+        return _topk_dense(q, pc, k_eff, rescore_exact, index_dtype)
     do_rescore = (pc.source is not None) if rescore_exact is None else bool(rescore_exact)
     if do_rescore and pc.source is None:
         raise ValueError("rescore_exact=True needs a PreparedCorpus built with keep_source=True")
@@ -265,6 +270,29 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
     if index_dtype != torch.int32:
         idx = idx.to(index_dtype)
     return scores, idx
+
+
+def _topk_dense(q: torch.Tensor, pc: PreparedCorpus, k: int, rescore_exact: Optional[bool], index_dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k > max_k(): dense scores (the same tensor-core contraction) + stable descending sort per query chunk; the k
+    best are re-scored exactly when the corpus kept its source (lists of up to 1024)."""
+    n_queries = q.shape[0]
+    do_rescore = ((pc.source is not None) if rescore_exact is None else bool(rescore_exact)) and k <= 1024
+    kprime = min(pc.n, k + max(8, k // 8), 1024) if do_rescore else k
+    chunk = max(1, (1 << 28) // max(pc.n, 1))
+    out_s = torch.empty((n_queries, k), dtype=torch.float32, device=pc.device)
+    out_i = torch.empty((n_queries, k), dtype=torch.int32, device=pc.device)
+    q_inv_all = None
+    if do_rescore and pc.metric == "cos":
+        _, q_inv_all = normalize_cast(q, pc.op, _lib.SIDE_QUERY, True, pc.eps)
+    for lo in range(0, n_queries, chunk):
+        sub = q[lo:lo + chunk]
+        dense = dense_scores(sub, pc)
+        s_sorted, i_sorted = torch.sort(dense, dim=1, descending=True, stable=True)
+        s_top, i_top = s_sorted[:, :kprime].contiguous(), (i_sorted[:, :kprime] + pc.idx_offset).to(torch.int32).contiguous()
+        if do_rescore:
+            s_top, i_top = rescore(sub, None if q_inv_all is None else q_inv_all[lo:lo + chunk], pc, i_top, k)
+        out_s[lo:lo + chunk], out_i[lo:lo + chunk] = s_top[:, :k], i_top[:, :k]
+    return out_s, (out_i if index_dtype == torch.int32 else out_i.to(index_dtype))
 
 
 def dense_scores(queries, corpus, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None) -> torch.Tensor:

@@ -81,7 +81,7 @@ def semantic_search(query_embeddings, corpus_embeddings, query_chunk_size: int =
     if device is None and isinstance(corpus_embeddings, torch.Tensor) and corpus_embeddings.is_cuda:
         device = corpus_embeddings.device
     pc = _prepared_for(corpus_embeddings, dtype, metric, device)
-    scores, idx = ops.topk(query_embeddings, pc, top_k)
+    scores, idx = ops.topk(query_embeddings, pc, top_k, dense_fallback=True)     # top_k > 120: dense pass + device sort
     s_host = scores.cpu().tolist()
     i_host = idx.cpu().tolist()
     return [[{"corpus_id": int(i), "score": float(s)} for s, i in zip(srow, irow) if i >= 0]

@@ -253,6 +253,11 @@ def test_edge_cases(m):
     assert exact.compare_topk(s, i, _device_scores(m, q, big, "bf16", 1e-12), 120, 2e-6).ok
     with pytest.raises(m.MmdError):
         m.topk(q.cuda(), big.cuda(), 121)
+    # ... unless the dense fallback is asked for (semantic_search does): exact lists of any length
+    s, i = m.topk(q.cuda(), big.cuda(), 300, dense_fallback=True)
+    assert tuple(i.shape) == (5, 300) and exact.compare_topk(s, i, exact.exact_scores(q, big), 300, tie_tol=2e-6).ok
+    hits = m.semantic_search(q[:2], big, top_k=1500)
+    assert len(hits[0]) == 1500 and hits[0][0]["corpus_id"] == int(exact.exact_topk(q[:1], big, 1)[1])
     with pytest.raises(RuntimeError):
         m.topk(torch.ones(2, 32).cuda(), big.cuda(), 3)           # dim mismatch, like torch.mm upstream
     # inner-product metric
