@@ -13,5 +13,7 @@ Modules
                  (PINNED: tests/golden/im2im_*.npz were produced by the reference's code, see make_golden.py)
   exact.py       batched float64 ground truth (normalise -> matmul -> ordered top-k) and the near-tie classifier
   evalmetrics.py restatement of the hits@k evaluation of src/evidence/experiment_{image,text}.py
+  fusion.py      float64 statement of the joint image+text score sum_m w_m * cos_m (no reference counterpart: PARITY
+                 UNPINNED) and a restatement of the reference's two-list concat + sort (text2text_retrieval.py:97-118)
   make_golden.py generator of tests/golden/*.npz (run in the build container, where /root/reference exists)
 """
