@@ -215,7 +215,10 @@ class ShardedCorpus:
         n_queries = q.shape[0]
         # (an empty shard goes through the same calls: every candidate is (-inf, -1))
         # peer memory + global stage order: the pruning thresholds are shared across the GPUs as well
-        share_thr = peer is not None and two_phase and self.share_thresholds
+        # (a shard's K'-th best bounds the global K'-th best only if the shard lists are as long as the global candidate
+        #  list: not the case for corpora so small that a shard holds fewer rows than that list)
+        kc = min(world * kp_glob, ops.overfetch_for(k_glob, self.n_total))
+        share_thr = peer is not None and two_phase and self.share_thresholds and kp_glob >= kc
         if peer is not None:
             ptrs, local = peer.slot(parity)                        # local: [world, cap, 2]
         # ... and when this shard can fill the common list width, the strip merge stores the raw candidate list straight
@@ -261,7 +264,6 @@ class ShardedCorpus:
                 # between the step's two barriers: every rank is past this step's contraction, nobody can have begun the
                 # next one -- the other parity's thresholds (used by the next step) are cleared here
                 peer.thr[1 - parity, :n_queries].zero_()
-            kc = min(world * kp_glob, ops.overfetch_for(k_glob, self.n_total))
             _, cand_glob = merged(g1, kp_glob, kc)                 # the global K' candidates, identical on every rank
             g2 = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand_glob, k_glob, d, dst_offset_pairs=off),
                           k_glob, n_queries * kp_glob)
