@@ -20,7 +20,7 @@ from .ops import (PreparedCorpus, prepare_corpus, topk, dense_scores, merge_topk
 from .postfilter import dedupe_by_score, hits_at_k
 from .semantic_search import semantic_search, cos_sim, dot_score, clear_cache
 from .image_corpus import ImageCorpus, ImageSimilarity, calculate_topk_accuracy_image_retrieval
-from .text_corpus import SemanticSimilarity
+from .text_corpus import SemanticSimilarity, calculate_topk_accuracy_text_retrieval
 from .sharded import ShardedCorpus, shard_bounds
 from .joint import JointCorpus, prepare_joint, topk_joint
 from .corpus_io import prepare_streamed, load_text_corpus, load_image_corpus
@@ -28,6 +28,6 @@ from .corpus_io import prepare_streamed, load_text_corpus, load_image_corpus
 __all__ = [
     "MmdError", "LIB_PATH", "PreparedCorpus", "prepare_corpus", "topk", "dense_scores", "merge_topk", "normalize_cast",
     "max_k", "profile_enable", "profile_collect", "launch_count", "dedupe_by_score", "hits_at_k", "semantic_search",
-    "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "SemanticSimilarity", "calculate_topk_accuracy_image_retrieval",
+    "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "SemanticSimilarity", "calculate_topk_accuracy_text_retrieval", "calculate_topk_accuracy_image_retrieval",
     "ShardedCorpus", "shard_bounds", "JointCorpus", "prepare_joint", "topk_joint", "prepare_streamed", "load_text_corpus", "load_image_corpus",
 ]

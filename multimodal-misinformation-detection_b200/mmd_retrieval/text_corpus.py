@@ -16,7 +16,7 @@ from typing import Callable, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import ops
-from .postfilter import dedupe_by_score
+from .postfilter import dedupe_by_score, hits_at_k
 
 
 def _decode(i) -> str:
@@ -55,17 +55,20 @@ class SemanticSimilarity:
             return torch.stack([torch.as_tensor(self.bi_encoder.encode(t)).reshape(-1).float() for t in queries])
         return ops._as_rows(queries)
 
-    def search_batch(self, queries, top_k: int, query_texts: Optional[Sequence[str]] = None) -> List[List[Tuple[str, float]]]:
-        """One deduped [(id, score)] list per claim.  queries: strings (needs the bi-encoder) or embeddings [Q,D]."""
+    def search_batch(self, queries, top_k: int, query_texts: Optional[Sequence[str]] = None, overfetch: Optional[int] = None,
+                     gold_ids: Optional[Sequence[str]] = None) -> List[List[Tuple[str, float]]]:
+        """One deduped [(id, score)] list per claim.  queries: strings (needs the bi-encoder) or embeddings [Q,D].
+        overfetch: hits per corpus = top_k * overfetch (5 in search, 10 in the evaluation script); gold_ids[q]: id that
+        the distinct-score filter must keep for claim q even if its score repeats (experiment_text.py:80)."""
         if isinstance(queries, str):
             queries = [queries]
         if query_texts is None and isinstance(queries, (list, tuple)) and queries and isinstance(queries[0], str):
             query_texts = list(queries)
         emb = self._embed(queries)
-        k_each = top_k * self.OVERFETCH
+        k_each = top_k * (self.OVERFETCH if overfetch is None else overfetch)
         lists = []
         for corpus in (self.train, self.test):
-            s, i = ops.topk(emb, corpus, k_each)
+            s, i = ops.topk(emb, corpus, k_each, dense_fallback=True)
             lists.append((s.cpu().tolist(), i.cpu().tolist()))
         out = []
         for qi in range(emb.shape[0]):
@@ -77,9 +80,25 @@ class SemanticSimilarity:
                     hits = sorted(((row, float(c)) for (row, _), c in zip(hits, cross)), key=lambda t: t[1], reverse=True)[:k_each]
                 results += [(_decode(ids[row]), score) for row, score in hits]
             ranked = sorted(results, key=lambda t: t[1], reverse=True)
-            out.append(dedupe_by_score(ranked, top_k))
+            gold = None if gold_ids is None else (lambda key, g=gold_ids[qi]: key == g)
+            out.append(dedupe_by_score(ranked, top_k, gold))
         return out
 
     def search(self, query: Union[str, torch.Tensor], top_k: int) -> List[Tuple[str, float]]:
         """The reference's signature: one claim in, [(id, score)] out (text2text_retrieval.py:49)."""
         return self.search_batch([query] if isinstance(query, str) else query, top_k)[0]
+
+
+def calculate_topk_accuracy_text_retrieval(similarity: SemanticSimilarity, queries, k_values: Sequence[int] = (1, 2, 5, 10),
+                                           query_texts: Optional[Sequence[str]] = None,
+                                           gold_ids: Optional[Sequence[str]] = None) -> dict:
+    """hits@k of every claim's paired evidence, the reference's text-retrieval evaluation
+    (src/evidence/experiment_text.py:11-106): top_k*10 hits from the train and from the test corpus, optional
+    cross-encoder re-rank, concatenation, descending sort, distinct-score filter that always keeps the gold evidence
+    `test_{query_id}`, then membership of the gold id in the first k entries.  All claims are searched in two fused GPU
+    calls instead of one call pair per claim."""
+    n = len(queries) if not isinstance(queries, torch.Tensor) else (1 if queries.dim() == 1 else queries.shape[0])
+    gold = [f"test_{i}" for i in range(n)] if gold_ids is None else list(gold_ids)
+    top_k = max(k_values)
+    lists = similarity.search_batch(queries, top_k, query_texts=query_texts, overfetch=10, gold_ids=gold)
+    return hits_at_k([[key for key, _ in lst] for lst in lists], gold, k_values)

@@ -462,6 +462,31 @@ def test_text_search_drop_in_matches_restated_reference_flow(m):
     assert [s for _, s in out[0]] == sorted({s for _, s in out[0]}, reverse=True) and out[0][0][1] == 6.0
 
 
+def test_text_topk_accuracy_matches_restated_reference_eval(m):
+    """calculate_topk_accuracy_text_retrieval (experiment_text.py:11-106) on Factify-shaped synthetic data -- every claim
+    has one planted evidence `test_{i}`, some evidences are exact duplicates of train rows (equal scores: the gold
+    exemption matters) -- against the same evaluation assembled from the restated semantic_search on the host."""
+    from oracle import evalmetrics
+    n_claims = 120
+    train, test = _data("text", 2500, 768, 101), _data("text", n_claims, 768, 102)
+    claims = test + 0.9 * _data("text", n_claims, 768, 103)          # noisy enough for hits@1 < 1
+    train[:30] = test[:30]                                           # duplicated evidence: same score as the gold row
+    train_ids = [f"train_{j}".encode() for j in range(2500)]
+    test_ids = [f"test_{j}".encode() for j in range(n_claims)]
+    ss = m.SemanticSimilarity(train.cuda(), train_ids, test.cuda(), test_ids)
+    got = m.calculate_topk_accuracy_text_retrieval(ss, claims)
+    lists = []
+    for qi in range(n_claims):
+        res = []
+        for corpus, ids in ((train, train_ids), (test, test_ids)):
+            res += [(ids[h["corpus_id"]].decode(), h["score"]) for h in st_util.semantic_search(claims[qi], corpus, top_k=100)[0]]
+        ranked = sorted(res, key=lambda t: t[1], reverse=True)
+        lists.append([key for key, _ in evalmetrics.dedupe_first_of_each_score(ranked, 10, gold=lambda key, qi=qi: key == f"test_{qi}")])
+    want = evalmetrics.hits_at_k(lists, [f"test_{i}" for i in range(n_claims)], (1, 2, 5, 10))
+    assert got == want, (got, want)
+    assert 0.2 < got[1] <= got[2] <= got[5] <= got[10] <= 1.0
+
+
 def test_device_dedupe_matches_reference_walk(m):
     """mmd_dedupe_scores vs the host restatement of the reference's distinct-score walk (with and without the gold
     exemption), on lists full of repeated scores."""
