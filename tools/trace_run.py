@@ -11,7 +11,8 @@ q = torch.randn(Q, D, device="cuda", generator=g)
 c = torch.randn(N, D, device="cuda", generator=g)
 if kind == "image":
     q, c = torch.relu(q), torch.relu(c)
-pc = m.prepare_corpus(c, dtype="bf16", keep_source=False)
+op = sys.argv[6] if len(sys.argv) > 6 else "bf16"
+pc = m.prepare_corpus(c, dtype=op, keep_source=False)
 for _ in range(5):
     m.topk(q, pc, k, rescore_exact=False)
 torch.cuda.synchronize()
