@@ -676,6 +676,8 @@ Schedule plan_schedule(int64_t Q, int64_t N, int kprime, int sms, int kblocks, i
   // restart charge: ~8k cycles against kblocks * 512 cycles of MMA per tile, at least a quarter tile
   double restart = 8000.0 / (static_cast<double>(kblocks > 0 ? kblocks : 1) * 512.0);
   if (restart < 0.25) restart = 0.25;
+  static const double forced_restart = [] { const char* e = getenv("MMD_RESTART_TILES"); return e ? atof(e) : 0.0; }();   // tuning knob
+  if (forced_restart > 0.0) restart = forced_restart;
   double best_cost = -1.0;
   int best_S = 1, best_T = s.n_n;
   int last_T = -1;
