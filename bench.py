@@ -68,6 +68,9 @@ def parse_args():
                          "launches on c3 at 1, 2 and 8 GPUs, where eager launches keep one fused-kernel timing per step")
     ap.add_argument("--rescore", default="global", choices=["global", "local"],
                     help="N>1: exact re-score after the global candidate merge (default) or per shard before the exchange")
+    ap.add_argument("--phases", type=int, default=0,
+                    help="1 GPU: launches per sweep of the corpus, the merged K-th best carried between them as pruning bound "
+                         "(0 = 4 for c5, 1 otherwise)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how the per-rank top-K lists are exchanged (peer-memory stores from the re-score kernel, or NCCL all-gather)")
     return ap.parse_args()
@@ -237,7 +240,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="auto",
-                     rescore="global"):
+                     rescore="global", phases=0):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
     parts = max(world, BUILT_FOR.get(name, 1))
@@ -277,6 +280,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         t1.record()
     torch.cuda.synchronize()
     prep_ms = t0.elapsed_time(t1)
+    sc.phases = phases if phases > 0 else (4 if name == "c5" else 1)
 
     def barrier():
         if world > 1:
@@ -408,13 +412,15 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
                                    "unit": "GB/s", "kernel_ms": kt, "bytes_per_launch": corpus_bytes}}
 
     ms_per_step = elapsed_ms / steps
-    fused_avg = sum(fused_ms) / len(fused_ms) if fused_ms else None
+    # fused-kernel time of one step: one launch, or the sum of the step's launches when the sweep is phased
+    per_step = max(1, round(len(fused_ms) / steps)) if fused_ms else 1
+    fused_avg = sum(fused_ms) / (len(fused_ms) / per_step) if fused_ms else None
     flops_per_launch = 2.0 * q_n * (hi - lo) * dim
     return {"q_n": q_n, "c_n": c_n, "c_total": c_total, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
             "ms_per_step": ms_per_step, "prep_ms": prep_ms, "fused_ms": fused_avg, "flops_per_launch": flops_per_launch,
             "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item()),
             "stream": stream,
-            "exchange": sc.exchange if world > 1 else "none (1 GPU)", "launch_mode": graph_note,
+            "exchange": sc.exchange if world > 1 else "none (1 GPU)", "launch_mode": graph_note, "phases": sc.phases if world == 1 else 1,
             "stage_order": (f"rescore after the global candidate merge" if rescore == "global" else "rescore per shard, one exchange") if world > 1 else "single shard"}
 
 
@@ -462,7 +468,7 @@ def run_ours(args):
     peaks = measured_peaks()
 
     res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange,
-                           graph=args.graph, rescore=args.rescore)
+                           graph=args.graph, rescore=args.rescore, phases=args.phases)
     extra = {}
     if world == 1 and not args.no_extra and args.workload != "c2":
         r2 = measure_workload(m, dist, torch, "c2", 1, 0, device, max(args.steps, 20), args.warmup)
@@ -493,7 +499,7 @@ def run_ours(args):
                                                            f" -- HERE: {world} rank(s) x one GPU's 1/{BUILT_FOR[args.workload]} share = {res['c_total']} rows"),
                        "queries": q_n, "corpus_rows": res["c_total"], "dim": dim, "top_k": k,
                        "corpus_rows_per_gpu": res["rows_local"], "parallelism": f"corpus row-sharded x{world}", "exchange": res["exchange"], "launch_mode": res["launch_mode"],
-                       "stage_order": res["stage_order"],
+                       "stage_order": res["stage_order"], "phases": res["phases"],
                        "l2": "operands exceed L2 (no flush needed)" if res["rows_local"] * dim * 2 > 126e6 else
                              "corpus shard fits L2; queries + source rows re-read per step",
                        "prep_ms": res["prep_ms"], "rescore": f"exact fp32 re-score of {overfetch_for(k, res['rows_local'])} over-fetched candidates per query",

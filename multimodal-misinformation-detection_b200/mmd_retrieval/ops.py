@@ -210,8 +210,50 @@ def rescore_pairs(q: torch.Tensor, q_inv: Optional[torch.Tensor], corpus: Prepar
     _lib.check(rc, "mmd_rescore_pairs")
 
 
+def _ordered_bound(scores: torch.Tensor, raw_scale: float) -> torch.Tensor:
+    """K-th best scores f32 [Q] -> the kernel's threshold encoding (order-preserving uint32 of the next float below, as
+    int64): what publish_threshold() writes for a bound learnt on the device."""
+    raw = (scores.float() * raw_scale + 0.0).contiguous()
+    u = raw.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    ordered = torch.where(u >= 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000)
+    ordered = torch.where(torch.isfinite(raw), ordered - 1, torch.zeros_like(ordered))      # -inf (short list): no bound
+    return ordered
+
+
+def topk_prepared_phased(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, k: int, phases: int
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """topk_prepared over `phases` contiguous row ranges of the corpus, one fused launch each, with the pruning
+    thresholds carried over AND tightened between launches: after every phase the lists found so far are merged and the
+    merged K-th best becomes every query's bound for the next phase.  Inside one launch a CTA only ever learns the K-th
+    best of single strips; the merged bound is an order of magnitude tighter on large corpora, which keeps the epilogue's
+    collect pass rare -- it matters where the contraction is fast and the lists long (fp8, K = 100: BASELINE configs[4])."""
+    dev = corpus.device
+    phases = max(1, min(int(phases), max(1, corpus.n // 65536)))
+    if phases == 1:
+        return topk_prepared(q_rows, n_queries, corpus, k)
+    raw_scale = 65536.0 if corpus.op == "fp8" else 1.0
+    thr = torch.zeros((n_queries,), dtype=torch.int32, device=dev)
+    thr_ptr = (thr.data_ptr(), [thr.data_ptr()])
+    best_s = best_i = None
+    for ph in range(phases):
+        lo, hi = (corpus.n * ph) // phases, (corpus.n * (ph + 1)) // phases
+        sub = PreparedCorpus(rows=corpus.rows[lo:hi], inv_norm=None, source=None, n=hi - lo, dim=corpus.dim, op=corpus.op,
+                             metric=corpus.metric, eps=corpus.eps, idx_offset=corpus.idx_offset + lo)
+        s, i = topk_prepared(q_rows, n_queries, sub, k, shared_thr=thr_ptr)
+        if best_s is None:
+            best_s, best_i = s, i
+        else:
+            best_s, best_i = merge_topk(torch.stack([best_s, s]), torch.stack([best_i, i]), k)
+        if ph + 1 < phases:
+            bound = _ordered_bound(best_s[:, k - 1], raw_scale)
+            cur = thr.to(torch.int64) & 0xFFFFFFFF
+            thr.copy_(torch.maximum(cur, bound).to(torch.int32))        # wraps into the same 32 bits
+    return best_s, best_i
+
+
 def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int] = None,
-                    shared_thr: Optional[Tuple[int, Sequence[int]]] = None, pair_dst: Optional[Tuple[Sequence[int], int]] = None):
+                    shared_thr: Optional[Tuple[int, Sequence[int]]] = None, pair_dst: Optional[Tuple[Sequence[int], int]] = None,
+                    phases: int = 1):
     """First half of the default path: K1 on the queries + fused tensor-core top-K' (K' = over-fetched k).
     Returns (q rows on the device, q inv_norm or None, raw scores f32 [Q,K'], candidate rows i32 [Q,K'])."""
     q = _as_rows(queries, pc.device)
@@ -220,14 +262,18 @@ def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int
     k_eff = min(k, pc.n)
     kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
     q_rows, q_inv = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
-    scores, idx = topk_prepared(q_rows, q.shape[0], pc, max(kprime, 1), shared_thr=shared_thr if pc.n > 0 else None,
-                                pair_dst=pair_dst if (pc.n > 0 and shared_thr is not None) else None)
+    if phases > 1 and shared_thr is None and pc.n > 0:
+        scores, idx = topk_prepared_phased(q_rows, q.shape[0], pc, max(kprime, 1), phases)
+    else:
+        scores, idx = topk_prepared(q_rows, q.shape[0], pc, max(kprime, 1), shared_thr=shared_thr if pc.n > 0 else None,
+                                    pair_dst=pair_dst if (pc.n > 0 and shared_thr is not None) else None)
     return q, (q_inv if pc.metric == "cos" else None), scores, idx
 
 
 def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None,
          rescore_exact: Optional[bool] = None, overfetch: Optional[int] = None,
-         index_dtype: torch.dtype = torch.int64, dense_fallback: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+         index_dtype: torch.dtype = torch.int64, dense_fallback: bool = False, phases: int = 1
+         ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k most similar corpus rows for every query.
 
     queries : [Q,D] (or [D]) tensor / ndarray / list, any device (moved to the corpus device).
@@ -236,6 +282,8 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
 
     rescore_exact (default: on when the corpus kept its source embeddings) over-fetches candidates with the
     tensor-core pass and recomputes their scores in fp32 from the original embeddings.
+    phases > 1: the corpus is swept in that many launches with the merged K-th best carried between them as pruning bound
+    (see topk_prepared_phased; for long lists over large corpora).
     dense_fallback: k beyond the fused selection's limit (120) is served by the dense tensor-core contraction plus a
     device-side stable sort of the score rows (query chunks of <= 1 GB of scores) -- off the hot path, for drop-in
     completeness only (the reference's largest list is top_k*10 = 100, experiment_text.py:26).
@@ -262,11 +310,12 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
     if do_rescore and pc.source is None:
         raise ValueError("rescore_exact=True needs a PreparedCorpus built with keep_source=True")
     if do_rescore:
-        q, q_inv, _, cand = topk_candidates(q, pc, k_eff, overfetch)
+        q, q_inv, _, cand = topk_candidates(q, pc, k_eff, overfetch, phases=phases)
         scores, idx = rescore(q, q_inv, pc, cand, k_eff)
     else:
         q_rows, _ = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
-        scores, idx = topk_prepared(q_rows, n_queries, pc, k_eff)
+        scores, idx = topk_prepared_phased(q_rows, n_queries, pc, k_eff, phases) if phases > 1 else \
+            topk_prepared(q_rows, n_queries, pc, k_eff)
     if index_dtype != torch.int32:
         idx = idx.to(index_dtype)
     return scores, idx

@@ -108,6 +108,7 @@ class ShardedCorpus:
             raise ValueError("rescore must be 'global' or 'local'")
         self.rescore = rescore
         self.share_thresholds = share_thresholds
+        self.phases = 1                   # single-GPU searches: launches per sweep of the shard (ops.topk_prepared_phased)
         self._exchange_req = exchange
         self.exchange = "nccl"            # what is actually in use; "peer" once symmetric memory is up on every rank
         self._peer: Optional[_PeerExchange] = None
@@ -166,7 +167,7 @@ class ShardedCorpus:
         k_glob = min(k, self.n_total)
         shard = self.shard
         if self.world == 1:
-            return ops.topk(queries, shard, k)
+            return ops.topk(queries, shard, k, phases=self.phases)
         if shard.source is None:
             return self._topk_generic(queries, k)
         dev = shard.device

@@ -305,6 +305,24 @@ def test_sharded_equals_unsharded(m):
     assert torch.equal(i.long(), want_i) and torch.equal(s, want_s)
 
 
+@pytest.mark.parametrize("op,k", [("bf16", 10), ("fp8", 100)])
+def test_phased_sweep_equals_single_launch(m, op, k):
+    """Several launches over contiguous row ranges with the merged K-th best carried between them as pruning bound give
+    the same lists as one launch (the bound only removes rows that cannot make the final list)."""
+    q, c = _data("text", 200, 768, 66), _data("text", 300_000, 768, 67)
+    c[299_999] = c[3]
+    q[0] = c[3] * 2
+    pc = m.prepare_corpus(c.cuda(), dtype=op, keep_source=False)
+    want_s, want_i = m.topk(q.cuda(), pc, k, rescore_exact=False)
+    for phases in (2, 4):
+        s, i = m.topk(q.cuda(), pc, k, rescore_exact=False, phases=phases)
+        assert torch.equal(i, want_i) and torch.equal(s, want_s), phases
+    pc2 = m.prepare_corpus(c.cuda(), dtype=op)
+    s, i = m.topk(q.cuda(), pc2, k, phases=3)
+    s1, i1 = m.topk(q.cuda(), pc2, k)
+    assert torch.equal(i, i1) and torch.equal(s, s1)
+
+
 def test_cuda_graph_replay_single_gpu(m):
     """ShardedCorpus.capture on one GPU: the whole step (K1, fused top-K', strip merge, re-score) replayed from a CUDA
     graph gives the same bits as the eager call, for fresh query batches copied into the static input."""
