@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the additional c2 measurement at N=1")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional c2 and one-claim-per-call measurements at N=1")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from CUDA graphs.  auto: only for the sub-millisecond single-GPU workloads (c1, c2), where "
                          "eager launches are host-bound (c2: 1.9 ms/step eager vs 0.73 ms replayed); measured equal to eager "
@@ -240,7 +240,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="auto",
-                     rescore="global", phases=0):
+                     rescore="global", phases=0, want_stream=True):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
     parts = max(world, BUILT_FOR.get(name, 1))
@@ -386,7 +386,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
 
     # ---- the reference's own calling pattern on the same resident corpus: ONE claim per call (HBM-bound corpus stream)
     stream = None
-    if world == 1 and kind == "text" and name == "c3":
+    if want_stream and world == 1 and kind == "text" and name == "c3":
         from mmd_retrieval import ops
         q1 = queries[:1].contiguous()
         for _ in range(30):
@@ -468,7 +468,7 @@ def run_ours(args):
     peaks = measured_peaks()
 
     res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange,
-                           graph=args.graph, rescore=args.rescore, phases=args.phases)
+                           graph=args.graph, rescore=args.rescore, phases=args.phases, want_stream=not args.no_extra)
     extra = {}
     if world == 1 and not args.no_extra and args.workload != "c2":
         r2 = measure_workload(m, dist, torch, "c2", 1, 0, device, max(args.steps, 20), args.warmup)
