@@ -65,3 +65,22 @@ def test_bad_arguments():
         m.prepare_corpus(torch.ones(3, 4), metric="l2")
     with pytest.raises(ValueError):
         m.topk(torch.ones(1, 4), torch.ones(3, 4), 0)
+
+
+def test_ordered_bound_matches_the_kernel_threshold_encoding():
+    """ops._ordered_bound must produce what the device's publish_threshold() writes: float_to_ordered(x + 0.0) - 1
+    (csrc/common.cuh), and no bound (0) for -inf, i.e. for lists that are not full yet."""
+    import struct
+
+    def device_encoding(f):
+        u = struct.unpack("<I", struct.pack("<f", f + 0.0))[0]
+        return ((~u) & 0xFFFFFFFF if u & 0x80000000 else u | 0x80000000) - 1
+
+    vals = [0.5, -0.25, 0.0, -0.0, 1e-30, -1e-30, 123.0, -7.5, 3.4e38]
+    got = ops._ordered_bound(torch.tensor(vals), 1.0).tolist()
+    assert got == [device_encoding(v) for v in vals]
+    assert ops._ordered_bound(torch.tensor([float("-inf")]), 1.0).tolist() == [0]
+    # order preserving: a larger score gives a larger bound; the fp8 path's 2^16 accumulator scale is applied first
+    s = torch.tensor([-2.0, -1.0, -0.5, 0.0, 0.25, 1.0])
+    b = ops._ordered_bound(s, 65536.0)
+    assert bool((b[1:] > b[:-1]).all()) and b.tolist() == [device_encoding(float(v) * 65536.0) for v in s]
