@@ -15,6 +15,7 @@ PyTorch is used for device memory and streams only; all arithmetic happens in li
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -64,6 +65,7 @@ def _as_rows(x, device: Optional[torch.device] = None) -> torch.Tensor:
     return x
 
 
+@functools.lru_cache(maxsize=None)
 def prepared_layout(op: str, dim: int) -> Tuple[int, int]:
     """(contraction length in operand elements, bytes per prepared row)."""
     kdim, row_bytes = C.c_int64(0), C.c_int64(0)
@@ -129,6 +131,7 @@ def prepare_corpus(corpus, dtype: str = "bf16", metric: str = "cos", eps: float 
                           n=c.shape[0], dim=c.shape[1], op=dtype, metric=metric, eps=eps, idx_offset=idx_offset)
 
 
+@functools.lru_cache(maxsize=None)
 def max_k() -> int:
     return int(_lib.load().mmd_topk_max_k())
 
