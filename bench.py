@@ -238,6 +238,134 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ result check + K1 line
+def parity_check(torch, dist, sc, queries, out, k, world, device, n_sample=64, tie_tol=5e-6, chunk=500_000):
+    """Independent check of the timed result on a sample of the queries, at every N: every rank scores the sampled queries
+    against its own shard's SOURCE embeddings with plain torch fp32 (F.normalize + matmul, TF32 off) -- no kernel of this
+    repository -- keeps its best k+16, the ranks' lists are all-gathered and merged, and the merged reference is compared
+    with the rows/scores the path returned under BASELINE.json's rule: index sets equal except at score near-ties
+    (|score - reference k-th score| <= tie_tol), scores within 1e-5 relative.  fp8 candidates are lossy by construction, so
+    that line also carries recall@k."""
+    import torch.nn.functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shard = sc.shard
+    joint = hasattr(shard, "sources")
+    q_mats = list(queries) if isinstance(queries, (list, tuple)) else [queries]
+    srcs = shard.sources if joint else [shard.source]
+    weights = shard.weights if joint else [1.0]
+    q_n = q_mats[0].shape[0]
+    n_sample = min(n_sample, q_n)
+    idx = torch.linspace(0, q_n - 1, n_sample, device=device).long()
+    kk = min(k + 16, sc.n_total)
+    qn = [F.normalize(qm[idx].float(), dim=1, eps=shard.eps) for qm in q_mats]
+    best_s = torch.full((n_sample, kk), float("-inf"), device=device)
+    best_i = torch.full((n_sample, kk), -1, dtype=torch.int64, device=device)
+    for lo in range(0, shard.n, chunk):
+        hi = min(shard.n, lo + chunk)
+        total = None
+        for qv, src, w in zip(qn, srcs, weights):
+            part = (qv @ F.normalize(src[lo:hi].float(), dim=1, eps=shard.eps).T) * float(w)
+            total = part if total is None else total + part
+        cs, ci = total.topk(min(kk, hi - lo), dim=1)
+        alls = torch.cat([best_s, cs], dim=1)
+        alli = torch.cat([best_i, ci + lo + shard.idx_offset], dim=1)
+        best_s, pos = alls.topk(kk, dim=1)
+        best_i = torch.gather(alli, 1, pos)
+    if world > 1:
+        gs = torch.empty((world,) + tuple(best_s.shape), device=device)
+        gi = torch.empty((world,) + tuple(best_i.shape), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gs.view(world * n_sample, kk), best_s.contiguous())
+        dist.all_gather_into_tensor(gi.view(world * n_sample, kk), best_i.contiguous())
+        alls, alli = gs.permute(1, 0, 2).reshape(n_sample, -1), gi.permute(1, 0, 2).reshape(n_sample, -1)
+        best_s, pos = alls.topk(kk, dim=1)
+        best_i = torch.gather(alli, 1, pos)
+    ref_s, ref_i = best_s.cpu().double(), best_i.cpu()
+    dev_s, dev_i = out[0][idx].cpu().double(), out[1][idx].cpu()
+    k_eff = min(k, sc.n_total)
+    violations, hits, max_rel = 0, 0, 0.0
+    for r in range(n_sample):
+        ref_rows = ref_i[r].tolist()
+        score_of = dict(zip(ref_rows, ref_s[r].tolist()))
+        ref_k = set(ref_rows[:k_eff])
+        dev = dev_i[r, :k_eff].tolist()
+        kth = float(ref_s[r, k_eff - 1])
+        hits += len(ref_k & set(dev))
+        bad = len(set(dev)) != k_eff
+        for d, sd in zip(dev, dev_s[r, :k_eff].tolist()):
+            if d in score_of:
+                max_rel = max(max_rel, abs(sd - score_of[d]) / max(abs(score_of[d]), 1e-30))
+            if d not in ref_k and (d not in score_of or score_of[d] < kth - tie_tol):
+                bad = True
+        for m_ in ref_k - set(dev):
+            if score_of[m_] > kth + tie_tol:
+                bad = True
+        violations += int(bad)
+    return {"checked": n_sample, "violations": violations, "recall_at_k": hits / float(n_sample * k_eff), "max_rel_score_err": max_rel,
+            "tie_tol": tie_tol, "reference": "torch fp32 F.normalize + matmul over the shard sources, per-rank top-(k+16), all-gathered and merged"}
+
+
+def k1_line(torch, m, sc, peaks, device, reps=20):
+    """K1 alone (fused normalise-and-cast of the resident corpus shard, warm), CUDA events on the launching stream: GB/s
+    against the measured HBM copy peak.  Algorithmic bytes per row: dim * sizeof(src) read + row_bytes + 4 written."""
+    from mmd_retrieval import ops, _lib
+    shard = sc.shard
+    src = getattr(shard, "source", None)
+    if src is None or isinstance(src, (list, tuple)) or shard.n == 0:
+        return None
+    src = src[: min(shard.n, 1_000_000)]
+    rows, dim = src.shape
+    _, row_bytes = ops.prepared_layout(shard.op, dim)
+    bufs = (torch.empty((rows, row_bytes), dtype=torch.uint8, device=device), torch.empty((rows,), dtype=torch.float32, device=device))
+    for _ in range(5):
+        ops.normalize_cast(src, shard.op, _lib.SIDE_CORPUS, True, shard.eps, out=bufs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.normalize_cast(src, shard.op, _lib.SIDE_CORPUS, True, shard.eps, out=bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = float(rows) * (dim * src.element_size() + row_bytes + 4)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"workload": f"K1 normalise+cast {rows} x {dim} {str(src.dtype).replace('torch.', '')} -> {shard.op}, warm, {reps} launches",
+            "ms_per_launch": ms,
+            "roofline": {"bound": "hbm", "kernel": "normalize_cast_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None, "bytes_per_launch": nbytes,
+                         "peak_source": peaks["source"] + ", HBM copy", "traffic": None}}
+
+
+def measure_fp8_peak(torch, device):
+    """Measured fp8 (e4m3 x e4m3 -> bf16, fp32 accumulate) tensor peak of THIS box: torch._scaled_mm 8192^3, best of 10 (burst)
+    and back to back for ~2 s (sustained) -- the same recipe MEASURED_PEAKS.json uses for bf16.  A library GEMM as the
+    roofline DENOMINATOR only; never on the product path."""
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=device).to(torch.float8_e4m3fn)
+        b = torch.randn((n, n), device=device).to(torch.float8_e4m3fn).t()
+        one = torch.ones((), device=device)
+        f = lambda: torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16)   # noqa: E731
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); f(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(2000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        return {"fp8_tflops_burst": flops / (best * 1e-3) / 1e12, "fp8_tflops_sustained": flops / (e0.elapsed_time(e1) / reps * 1e-3) / 1e12,
+                "how": "torch._scaled_mm e4m3 8192^3: best of 10 (burst), back to back for ~2 s (sustained), measured in this run"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="auto",
                      rescore="global", phases=0, want_stream=True):
@@ -255,7 +383,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         queries = [make_rows("text", q_n, half, 5, device), make_rows("text", q_n, half, 6, device)]
         torch.cuda.synchronize()
         t0.record()
-        sc = ShardedCorpus.from_joint(corp, c_total, lo, weights=(0.5, 0.5), dtype=op, eps=eps)
+        sc = ShardedCorpus.from_joint(corp, c_total, lo, weights=(0.5, 0.5), dtype=op, eps=eps, exchange=exchange, rescore=rescore)
         t1.record()
     elif name == "c5":
         from mmd_retrieval import prepare_streamed
@@ -289,6 +417,14 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     def step():
         return sc.topk(queries, k)
 
+    def run_steps(n):
+        """n steps on the device-resident batch through the pipelined stream API (successive batches overlap: with several
+        GPUs the exchange tail of one batch hides under the contraction of the next); returns the last result."""
+        last = None
+        for last in sc.topk_stream((queries for _ in range(n)), k):
+            pass
+        return last
+
     # the clock sampler (an nvidia-smi child process) comes up BEFORE the warm-up: its start-up (fork, NVML init, driver
     # locks) stalls kernel launches for tens of milliseconds and must not fall into a timed region that is itself that short
     sampler = ClockSampler(device.index)
@@ -296,8 +432,8 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         sampler.start()
         sampler.wait_first(3.0)
 
-    for _ in range(warmup):
-        step()
+    step()
+    run_steps(max(1, warmup))
     torch.cuda.synchronize()
     barrier()
 
@@ -342,8 +478,11 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     torch.cuda.synchronize()
     barrier()
     e0.record()
-    for _ in range(steps):
-        out = step()
+    if graphed is not None:
+        for _ in range(steps):
+            out = step()
+    else:
+        out = run_steps(steps)
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -361,21 +500,21 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     e2e = None
     if want_e2e:
         q_host = [x.cpu().pin_memory() for x in queries] if isinstance(queries, list) else queries.cpu().pin_memory()
-        res_s = torch.empty((q_n, k), dtype=torch.float32).pin_memory()
-        res_i = torch.empty((q_n, k), dtype=torch.int64).pin_memory()
 
-        def e2e_step():
-            s, i = graphed(q_host) if graphed is not None else sc.topk(q_host, k)   # H2D of the queries happens inside the call
-            res_s.copy_(s, non_blocking=True)
-            res_i.copy_(i, non_blocking=True)
-            torch.cuda.synchronize()
+        def e2e_steps(n):
+            """n batches: pinned host queries in (H2D inside the call), pinned host results out, through the public stream API:
+            the upload of batch i+1, the search of batch i and the read-back of batch i-1 overlap."""
+            got = 0
+            for hs, hi in sc.topk_stream((q_host for _ in range(n)), k, to_host=True):
+                got += hs.shape[0]
+            return got
 
-        for _ in range(max(1, warmup // 2)):
-            e2e_step()
+        e2e_steps(max(2, warmup // 2))
+        torch.cuda.synchronize()
         barrier()
         w0 = time.perf_counter()
-        for _ in range(steps):
-            e2e_step()
+        assert e2e_steps(steps) == q_n * steps
+        torch.cuda.synchronize()
         barrier()
         w = torch.tensor([time.perf_counter() - w0], device=device, dtype=torch.float64)
         if world > 1:
@@ -383,6 +522,9 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         e2e = {"value": q_n * steps / float(w.item()), "unit": "queries/s",
                "h2d_bytes_per_step": q_n * dim * 4, "d2h_bytes_per_step": q_n * k * (4 + 8),
                "ms_per_step": float(w.item()) * 1e3 / steps}
+
+    # ---- are the timed results right?  (every N; see parity_check)
+    parity = parity_check(torch, dist, sc, queries, out, k, world, device)
 
     # ---- the reference's own calling pattern on the same resident corpus: ONE claim per call (HBM-bound corpus stream)
     stream = None
@@ -418,33 +560,44 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
     flops_per_launch = 2.0 * q_n * (hi - lo) * dim
     return {"q_n": q_n, "c_n": c_n, "c_total": c_total, "dim": dim, "k": k, "op": op, "value": q_n / (ms_per_step * 1e-3),
             "ms_per_step": ms_per_step, "prep_ms": prep_ms, "fused_ms": fused_avg, "flops_per_launch": flops_per_launch,
-            "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "checksum": float(out[0].sum().item()),
+            "launches": launches, "clocks": clocks, "e2e": e2e, "rows_local": hi - lo, "parity": parity, "sc": sc,
             "stream": stream,
             "exchange": sc.exchange if world > 1 else "none (1 GPU)", "launch_mode": graph_note, "phases": sc.phases if world == 1 else 1,
-            "stage_order": (f"rescore after the global candidate merge" if rescore == "global" else "rescore per shard, one exchange") if world > 1 else "single shard"}
+            "stage_order": (("three flag-synchronised stages per rank (candidates -> merge + re-score of owned candidates -> finish), "
+                             f"{len(sc._sub_sizes(q_n))} pipelined sub-batches per call") if sc.exchange == "peer" else
+                            ("rescore after the global candidate merge" if rescore == "global" else "rescore per shard, one exchange"))
+            if world > 1 else "single shard"}
 
 
-def roofline_of(res, peaks, name):
+def roofline_of(res, peaks, name, fp8_peak=None):
+    """Roofline object of the dominant kernel.  `frac` is ALWAYS against the BURST peak (the timed region of a default run is
+    a fraction of a second of back-to-back launches at boost clocks, not a power-settled multi-second loop); the fraction of
+    the sustained peak and of the datasheet number are printed beside it."""
     if not res["fused_ms"]:
         return None
     achieved = res["flops_per_launch"] / (res["fused_ms"] * 1e-3) / 1e12
-    # a kernel timed inside a long power-capped step -> sustained peak; a sub-millisecond step -> burst peak
-    long_step = res["ms_per_step"] >= 5.0
-    peak = peaks["tflops_sustained"] if long_step else peaks["tflops_burst"]
-    src = peaks["source"] + (", sustained" if long_step else ", burst")
-    spec = 2250.0
-    if res["op"] == "fp8":
-        # MEASURED_PEAKS.json holds no fp8 figure: the e4m3 tensor pipe is nominally 2x the bf16 one
-        peak, spec, src = 2.0 * peak, 4500.0, src + " bf16 x 2 (no measured fp8 peak; nominal fp8:bf16 ratio)"
-    traffic = None
+    fp8 = res["op"] == "fp8"
+    spec = 4500.0 if fp8 else 2250.0
+    if fp8 and fp8_peak and "fp8_tflops_burst" in fp8_peak:
+        burst, sustained = fp8_peak["fp8_tflops_burst"], fp8_peak["fp8_tflops_sustained"]
+        src = "measured in this run: " + fp8_peak["how"]
+    elif fp8:
+        burst, sustained = 2.0 * peaks["tflops_burst"], 2.0 * peaks["tflops_sustained"]
+        src = peaks["source"] + " bf16 x 2 (fp8 peak measurement unavailable: " + str((fp8_peak or {}).get("error", "not run")) + ")"
+    else:
+        burst, sustained = peaks["tflops_burst"], peaks["tflops_sustained"]
+        src = peaks["source"] + ", cuBLAS bf16 8192^3"
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and res["rows_local"] == res["c_n"]:      # the capture is of the unsharded launch
         with open(tpath) as f:
             traffic = json.load(f).get(name)
-    return {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": src,
+        if traffic is not None:
+            traffic_source = "stored ncu --set full capture of this launch shape (profiles/traffic.json), not measured in this run"
+    return {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+            "frac": achieved / burst, "traffic": traffic, "traffic_source": traffic_source, "peak_source": src + ", burst",
             "kernel_ms": res["fused_ms"], "flops_per_launch": res["flops_per_launch"],
-            "frac_of_burst": achieved / (peaks["tflops_burst"] * (2.0 if res["op"] == "fp8" else 1.0)), "frac_of_spec": achieved / spec, "spec_tflops": spec}
+            "peak_sustained": sustained, "frac_of_sustained": achieved / sustained, "frac_of_spec": achieved / spec, "spec_tflops": spec}
 
 
 def run_ours(args):
@@ -467,13 +620,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     peaks = measured_peaks()
 
+    fp8_peak = None
+    if WORKLOADS[args.workload][4] == "fp8":
+        fp8_peak = measure_fp8_peak(torch, device)                 # before the corpus fills the HBM; every rank (keeps them in step)
     res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange,
                            graph=args.graph, rescore=args.rescore, phases=args.phases, want_stream=not args.no_extra)
     extra = {}
+    if world == 1 and not args.no_extra:
+        k1 = k1_line(torch, m, res["sc"], peaks, device)
+        if k1:
+            extra["k1"] = k1
+    res.pop("sc", None)
     if world == 1 and not args.no_extra and args.workload != "c2":
         r2 = measure_workload(m, dist, torch, "c2", 1, 0, device, max(args.steps, 20), args.warmup)
+        r2.pop("sc", None)
         extra["c2"] = {"workload": NAMES["c2"], "value": r2["value"], "unit": "queries/s", "ms_per_step": r2["ms_per_step"],
-                       "e2e": r2["e2e"], "roofline": roofline_of(r2, peaks, "c2"), "prep_ms": r2["prep_ms"]}
+                       "e2e": r2["e2e"], "roofline": roofline_of(r2, peaks, "c2"), "prep_ms": r2["prep_ms"], "parity": r2["parity"],
+                       "launch_mode": r2["launch_mode"]}
 
     if res.get("stream"):
         st = res["stream"]
@@ -504,11 +667,13 @@ def run_ours(args):
                              "corpus shard fits L2; queries + source rows re-read per step",
                        "prep_ms": res["prep_ms"], "rescore": f"exact fp32 re-score of {overfetch_for(k, res['rows_local'])} over-fetched candidates per query",
                        "peaks": peaks["source"]},
-            "roofline": roofline_of(res, peaks, args.workload),
+            "roofline": roofline_of(res, peaks, args.workload, fp8_peak),
             "cpu_baseline": cpu,
             "e2e": res["e2e"],
+            "parity": res["parity"],
             "gpu_launches": res["launches"],
             "clocks": res["clocks"],
+            "build": m._lib.build_info(),
         }
         if extra:
             line["also"] = extra

@@ -174,6 +174,56 @@ MMD_API int mmd_rescore_joint(int n_seg, const void* const* q_src_host, const in
                       const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
                       int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, void* stream);
 
+/* mmd_rescore_joint with the packed multi-destination output of mmd_rescore_pairs. */
+MMD_API int mmd_rescore_joint_pairs(int n_seg, const void* const* q_src_host, const int* q_dtype_host,
+                            const int64_t* q_stride_host, const float* const* q_inv_host, const void* const* c_src_host,
+                            const int* c_dtype_host, const int64_t* c_stride_host, const float* const* c_inv_host,
+                            const int* dim_host, const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx,
+                            int k_in, int64_t idx_offset, int k_out, void* const* dst_host, int n_dst,
+                            int64_t dst_offset_pairs, void* stream);
+
+/* ---- row-sharded corpus: one search step = three kernels per rank, synchronised through flags in peer memory -------
+ * One process per GPU; the corpus rows are split over `world` ranks, the queries are replicated.  No reference
+ * counterpart (single process): the step stands where sentence_transformers.util.semantic_search merges its corpus
+ * chunks with a per-query heap (call sites src/evidence/text2text_retrieval.py:56-64, experiment_text.py:25-33).
+ *
+ * Synchronisation contract shared by the three calls: a STAGE owns a device word pair sync_state = {launches completed,
+ * blocks finished} (zero-initialised by the caller, then only touched by the library).  A producing stage writes
+ * (launches completed + 1) into arrive_flags_host[i] (one DEVICE pointer per rank: this rank's word in that rank's flag
+ * array, peer-mapped) when its last block is done; a consuming stage spins at its start until wait_flags[0..n_wait)
+ * (LOCAL flag array, one word per rank) have all reached (its own launches completed + 1).  Every rank must launch the
+ * same sequence of stages.  A wait that lasts more than 4 s traps the kernel (CUDA error at the next synchronisation).
+ *
+ * Stage C: mmd_topk_scores_shared, plus: the strip merge stores this rank's candidate list as packed pairs at pair
+ * pair_offset + q * pair_width + i (i < pair_width; entries beyond the k the shard can fill are empties) into every
+ * destination and arrives on arrive_flags_host.  n_thr = 0 keeps the pruning thresholds private to the launch; with
+ * n_thr > 0 and reset_thr != 0 thr_local[0..Q) is zeroed on `stream` first (bounds a faster peer has already published
+ * for this step are lost, which only weakens the pruning). */
+MMD_API int mmd_sharded_candidates(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
+                           int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                           size_t workspace_bytes, uint32_t* thr_local, void* const* thr_all_host, int n_thr, int reset_thr,
+                           void* const* pair_dst_host, int n_pair_dst, int64_t pair_offset, int pair_width,
+                           void* const* arrive_flags_host, int n_arrive, uint32_t* sync_state, void* stream);
+
+/* Stage X: wait; merge the `parts` sorted candidate lists of every query (gathered: part p starts p * part_stride_pairs
+ * pairs in, [Q][k_in] pairs each) into the global candidate list of kc entries (identical on every rank); re-score in
+ * fp32 -- modalities / source tables exactly as mmd_rescore_joint, n_seg = 1 with weight 1 is the plain cosine -- the
+ * candidates whose global row lies in [idx_offset, idx_offset + N), and store each {exact score bits, row} at pair
+ * dst_offset_pairs + q * kc + (position in the global list) into every destination (every rank's re-score buffer);
+ * empty positions are written to dst_host[own_dst] only.  Arrives on arrive_flags_host. */
+MMD_API int mmd_exchange_rescore(const void* gathered, int parts, int64_t part_stride_pairs, int64_t Q, int k_in, int kc,
+                         int n_seg, const void* const* q_src_host, const int* q_dtype_host, const int64_t* q_stride_host,
+                         const float* const* q_inv_host, const void* const* c_src_host, const int* c_dtype_host,
+                         const int64_t* c_stride_host, const float* const* c_inv_host, const int* dim_host,
+                         const float* weight_host, int64_t N, int64_t idx_offset, void* const* dst_host, int n_dst,
+                         int own_dst, int64_t dst_offset_pairs, const uint32_t* wait_flags, int n_wait,
+                         void* const* arrive_flags_host, int n_arrive, uint32_t* sync_state, void* stream);
+
+/* Stage F: wait; sort the kc re-scored candidates of every query (rescored: [Q][kc] pairs) and write the k_out best:
+ * out_scores f32 [Q,k_out], out_idx i32 or (idx_is_i64 != 0) i64 [Q,k_out]; missing entries are (-inf, -1). */
+MMD_API int mmd_exchange_finish(const void* rescored, int64_t Q, int kc, int k_out, float* out_scores, void* out_idx,
+                        int idx_is_i64, const uint32_t* wait_flags, int n_wait, uint32_t* sync_state, void* stream);
+
 /* ---- distinct-score filter of ranked lists ---------------------------------------------------- */
 /* scores/idx [Q, k_in] descending (as every entry point above returns them).  Keeps, per query, the first entry of every
  * distinct score -- and any entry whose row equals gold_idx[q] (gold_idx nullable; -1 = none) -- until top_k are kept:
@@ -194,6 +244,9 @@ MMD_API int mmd_profile_collect(float* ms_host, int cap);
 
 /* Launch counter: number of kernels this library has launched in this process (bench evidence). */
 MMD_API int64_t mmd_launch_count(void);
+
+/* Provenance of this binary: "src=<sha256 of csrc/*, include/*, build flags> nvcc=<version> arch=sm_100a ..." */
+MMD_API const char* mmd_build_info(void);
 
 #ifdef __cplusplus
 }

@@ -64,3 +64,8 @@ extern "C" int mmd_device_check(void) {
 }
 
 extern "C" int64_t mmd_launch_count(void) { return mmd::g_launches.load(std::memory_order_relaxed); }
+
+#ifndef MMD_BUILD_INFO
+#define MMD_BUILD_INFO "src=unknown (built without build.py)"
+#endif
+extern "C" const char* mmd_build_info(void) { return MMD_BUILD_INFO; }

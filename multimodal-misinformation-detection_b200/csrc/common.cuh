@@ -41,6 +41,7 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~stati
 struct PairOut {
   int2* dst[16];
   int n;
+  int width;        // pairs per query in the destinations (>= the list length; the surplus is filled with empties); 0 = list length
   int64_t offset;
 };
 

@@ -13,62 +13,12 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "rescore_common.cuh"
 
 namespace mmd {
 namespace {
 
 constexpr int kMaxCand = 1024;
-
-template <typename T>
-__device__ __forceinline__ float cvt(T v);
-template <>
-__device__ __forceinline__ float cvt<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ float cvt<__half>(__half v) { return __half2float(v); }
-template <>
-__device__ __forceinline__ float cvt<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-template <typename T>
-struct Vec {
-  static constexpr int kElems = 16 / sizeof(T);
-};
-
-template <typename TQ, typename TC>
-__device__ __forceinline__ float warp_dot(const TQ* __restrict__ a, const TC* __restrict__ b, int dim, int lane,
-                                          bool vec_ok) {
-  float acc = 0.0f;
-  if (vec_ok) {
-    // 8 elements per lane per step; both rows 16-byte aligned, dim % 8 == 0
-    for (int i = lane * 8; i < dim; i += 256) {
-      float x[8], y[8];
-      if constexpr (sizeof(TQ) == 4) {
-        const float4 u = *reinterpret_cast<const float4*>(a + i), w = *reinterpret_cast<const float4*>(a + i + 4);
-        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
-      } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
-        const TQ* p = reinterpret_cast<const TQ*>(&u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = cvt<TQ>(p[j]);
-      }
-      if constexpr (sizeof(TC) == 4) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(b + i)), w = __ldg(reinterpret_cast<const float4*>(b + i + 4));
-        y[0] = u.x; y[1] = u.y; y[2] = u.z; y[3] = u.w; y[4] = w.x; y[5] = w.y; y[6] = w.z; y[7] = w.w;
-      } else {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(b + i));
-        const TC* p = reinterpret_cast<const TC*>(&u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = cvt<TC>(p[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc = fmaf(x[j], y[j], acc);
-    }
-  } else {
-    for (int i = lane; i < dim; i += 32) acc = fmaf(cvt<TQ>(a[i]), cvt<TC>(b[i]), acc);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  return acc;
-}
 
 // Where a re-scored list goes: separate score / index arrays (the plain contract) and/or packed
 // {score bits, global row} pairs written to up to kMaxPairDst buffers -- the local send buffer of the all-gather,
@@ -212,27 +162,9 @@ namespace {
 // ---------------------------------------------------------------- joint (multi-modality) re-score
 // score(q, c) = sum_m weight_m * <q_m, c_m> * q_inv_m[q] * c_inv_m[c]  over up to kMaxSeg modalities, each with its own
 // embeddings (own dim / dtype / stride).  Element types are switched at run time (uniform per segment).
-constexpr int kMaxSeg = 4;
-struct Segments {
-  const void* q_src[kMaxSeg];
-  const void* c_src[kMaxSeg];
-  const float* q_inv[kMaxSeg];
-  const float* c_inv[kMaxSeg];
-  int64_t q_stride[kMaxSeg], c_stride[kMaxSeg];
-  int dim[kMaxSeg], q_dtype[kMaxSeg], c_dtype[kMaxSeg];
-  float weight[kMaxSeg];
-  int n;
-};
-
-__device__ __forceinline__ float load_rt(const void* base, int dtype, int64_t i) {
-  if (dtype == MMD_SRC_F32) return static_cast<const float*>(base)[i];
-  if (dtype == MMD_SRC_F16) return __half2float(static_cast<const __half*>(base)[i]);
-  return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
-}
-
 __global__ void __launch_bounds__(128)
 rescore_multi_kernel(Segments sg, int64_t N, const int32_t* __restrict__ cand_idx, int k_in, int64_t idx_offset, int k_out,
-                     float* __restrict__ out_s, int32_t* __restrict__ out_i) {
+                     float* __restrict__ out_s, int32_t* __restrict__ out_i, PairDst pairs) {
   __shared__ uint64_t keys[kMaxCand];
   const int64_t q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,24 +173,12 @@ rescore_multi_kernel(Segments sg, int64_t N, const int32_t* __restrict__ cand_id
     uint64_t key = 0ull;
     const int64_t row = static_cast<int64_t>(gi) - idx_offset;
     if (gi >= 0 && row >= 0 && row < N) {
-      float total = 0.0f;
-      for (int m = 0; m < sg.n; ++m) {
-        float acc = 0.0f;
-        const int64_t qo = q * sg.q_stride[m], co = row * sg.c_stride[m];
-        for (int i = lane; i < sg.dim[m]; i += 32)
-          acc = fmaf(load_rt(sg.q_src[m], sg.q_dtype[m], qo + i), load_rt(sg.c_src[m], sg.c_dtype[m], co + i), acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const float qi = sg.q_inv[m] != nullptr ? sg.q_inv[m][q] : 1.0f;
-        const float ci = sg.c_inv[m] != nullptr ? sg.c_inv[m][row] : 1.0f;
-        total = fmaf(sg.weight[m], acc * qi * ci, total);
-      }
+      const float total = segments_score(sg, q, row, lane);
       key = make_key(total, static_cast<uint32_t>(gi));
     }
     if (lane == 0) keys[j] = key;
   }
   __syncthreads();
-  PairDst none{};
   for (int j = threadIdx.x; j < k_in; j += 128) {
     const uint64_t mine = keys[j];
     int rank = 0;
@@ -269,12 +189,41 @@ rescore_multi_kernel(Segments sg, int64_t N, const int32_t* __restrict__ cand_id
     if (rank < k_out) {
       const float sc = mine == 0ull ? __int_as_float(0xff800000) : key_score(mine);
       const int32_t ix = mine == 0ull ? -1 : static_cast<int32_t>(key_row(mine));
-      emit(out_s, out_i, none, q * k_out + rank, sc, ix);
+      emit(out_s, out_i, pairs, q * k_out + rank, sc, ix);
     }
   }
-  for (int i = k_in + threadIdx.x; i < k_out; i += 128) emit(out_s, out_i, none, q * k_out + i, __int_as_float(0xff800000), -1);
+  for (int i = k_in + threadIdx.x; i < k_out; i += 128) emit(out_s, out_i, pairs, q * k_out + i, __int_as_float(0xff800000), -1);
 }
 
+}  // namespace
+}  // namespace mmd
+
+namespace mmd {
+namespace {
+int rescore_joint_any(int n_seg, const void* const* q_src_host, const int* q_dtype_host, const int64_t* q_stride_host,
+                      const float* const* q_inv_host, const void* const* c_src_host, const int* c_dtype_host,
+                      const int64_t* c_stride_host, const float* const* c_inv_host, const int* dim_host,
+                      const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
+                      int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, const PairDst& pairs, void* stream,
+                      const char* who) {
+  MMD_REQUIRE(Q >= 0 && N >= 0 && k_in > 0 && k_out > 0 && k_in <= kMaxCand, "%s: Q=%lld N=%lld k_in=%d k_out=%d", who,
+              (long long)Q, (long long)N, k_in, k_out);
+  if (Q == 0) return MMD_OK;
+  MMD_REQUIRE(cand_idx != nullptr, "%s: null candidate list", who);
+  MMD_REQUIRE((out_scores != nullptr && out_idx != nullptr) || (out_scores == nullptr && out_idx == nullptr && pairs.n > 0),
+              "%s: no output buffer", who);
+  Segments sg{};
+  int rc = fill_segments(&sg, n_seg, q_src_host, q_dtype_host, q_stride_host, q_inv_host, c_src_host, c_dtype_host, c_stride_host,
+                         c_inv_host, dim_host, weight_host, N, who);
+  if (rc != MMD_OK) return rc;
+  rc = mmd_device_check();
+  if (rc != MMD_OK) return rc;
+  rescore_multi_kernel<<<static_cast<unsigned>(Q), 128, 0, static_cast<cudaStream_t>(stream)>>>(sg, N, cand_idx, k_in, idx_offset,
+                                                                                                 k_out, out_scores, out_idx, pairs);
+  count_launch();
+  MMD_CUDA_OK(cudaGetLastError());
+  return MMD_OK;
+}
 }  // namespace
 }  // namespace mmd
 
@@ -283,35 +232,34 @@ extern "C" int mmd_rescore_joint(int n_seg, const void* const* q_src_host, const
                                  const int64_t* c_stride_host, const float* const* c_inv_host, const int* dim_host,
                                  const float* weight_host, int64_t Q, int64_t N, const int32_t* cand_idx, int k_in,
                                  int64_t idx_offset, int k_out, float* out_scores, int32_t* out_idx, void* stream) {
+  mmd::PairDst none{};
+  MMD_REQUIRE(Q == 0 || (out_scores != nullptr && out_idx != nullptr), "mmd_rescore_joint: null output");
+  return mmd::rescore_joint_any(n_seg, q_src_host, q_dtype_host, q_stride_host, q_inv_host, c_src_host, c_dtype_host, c_stride_host,
+                                c_inv_host, dim_host, weight_host, Q, N, cand_idx, k_in, idx_offset, k_out, out_scores, out_idx,
+                                none, stream, "mmd_rescore_joint");
+}
+
+extern "C" int mmd_rescore_joint_pairs(int n_seg, const void* const* q_src_host, const int* q_dtype_host,
+                                       const int64_t* q_stride_host, const float* const* q_inv_host,
+                                       const void* const* c_src_host, const int* c_dtype_host, const int64_t* c_stride_host,
+                                       const float* const* c_inv_host, const int* dim_host, const float* weight_host,
+                                       int64_t Q, int64_t N, const int32_t* cand_idx, int k_in, int64_t idx_offset, int k_out,
+                                       void* const* dst_host, int n_dst, int64_t dst_offset_pairs, void* stream) {
   using namespace mmd;
-  MMD_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, "mmd_rescore_joint: n_seg=%d (1..%d)", n_seg, kMaxSeg);
-  MMD_REQUIRE(Q >= 0 && N >= 0 && k_in > 0 && k_out > 0 && k_in <= kMaxCand, "mmd_rescore_joint: Q=%lld N=%lld k_in=%d k_out=%d",
-              (long long)Q, (long long)N, k_in, k_out);
-  if (Q == 0) return MMD_OK;
-  MMD_REQUIRE(cand_idx != nullptr && out_scores != nullptr && out_idx != nullptr, "mmd_rescore_joint: null buffer");
-  Segments sg{};
-  sg.n = n_seg;
-  for (int m = 0; m < n_seg; ++m) {
-    MMD_REQUIRE(q_src_host[m] != nullptr && (c_src_host[m] != nullptr || N == 0) && dim_host[m] > 0,
-                "mmd_rescore_joint: segment %d has a null buffer or non-positive dim", m);
-    MMD_REQUIRE(q_dtype_host[m] >= 0 && q_dtype_host[m] <= 2 && c_dtype_host[m] >= 0 && c_dtype_host[m] <= 2,
-                "mmd_rescore_joint: segment %d has an unknown dtype", m);
-    MMD_REQUIRE(q_stride_host[m] >= dim_host[m] && (c_stride_host[m] >= dim_host[m] || N == 0),
-                "mmd_rescore_joint: segment %d row stride smaller than dim", m);
-    sg.q_src[m] = q_src_host[m]; sg.c_src[m] = c_src_host[m];
-    sg.q_inv[m] = q_inv_host != nullptr ? q_inv_host[m] : nullptr;
-    sg.c_inv[m] = c_inv_host != nullptr ? c_inv_host[m] : nullptr;
-    sg.q_stride[m] = q_stride_host[m]; sg.c_stride[m] = c_stride_host[m];
-    sg.dim[m] = dim_host[m]; sg.q_dtype[m] = q_dtype_host[m]; sg.c_dtype[m] = c_dtype_host[m];
-    sg.weight[m] = weight_host[m];
+  MMD_REQUIRE(dst_host != nullptr && n_dst >= 1 && n_dst <= kMaxPairDst, "mmd_rescore_joint_pairs: n_dst=%d (1..%d)", n_dst,
+              kMaxPairDst);
+  MMD_REQUIRE(dst_offset_pairs >= 0, "mmd_rescore_joint_pairs: negative offset");
+  PairDst pairs{};
+  pairs.n = n_dst;
+  pairs.offset = dst_offset_pairs;
+  for (int d = 0; d < n_dst; ++d) {
+    MMD_REQUIRE(dst_host[d] != nullptr && reinterpret_cast<uintptr_t>(dst_host[d]) % 8 == 0,
+                "mmd_rescore_joint_pairs: destination %d is null or not 8-byte aligned", d);
+    pairs.dst[d] = static_cast<int2*>(dst_host[d]);
   }
-  int rc = mmd_device_check();
-  if (rc != MMD_OK) return rc;
-  rescore_multi_kernel<<<static_cast<unsigned>(Q), 128, 0, static_cast<cudaStream_t>(stream)>>>(sg, N, cand_idx, k_in, idx_offset,
-                                                                                                 k_out, out_scores, out_idx);
-  count_launch();
-  MMD_CUDA_OK(cudaGetLastError());
-  return MMD_OK;
+  return rescore_joint_any(n_seg, q_src_host, q_dtype_host, q_stride_host, q_inv_host, c_src_host, c_dtype_host, c_stride_host,
+                           c_inv_host, dim_host, weight_host, Q, N, cand_idx, k_in, idx_offset, k_out, nullptr, nullptr, pairs,
+                           stream, "mmd_rescore_joint_pairs");
 }
 
 namespace mmd {

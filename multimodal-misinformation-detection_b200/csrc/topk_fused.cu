@@ -28,13 +28,15 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 
 namespace mmd {
 
 int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
                        int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream,
-                       const PairOut* po = nullptr);
+                       const PairOut* po = nullptr, const PeerArrive* arrive = nullptr);
+int fill_arrive(PeerArrive* a, void* const* flags_host, int n, uint32_t* state, const char* who);
 
 namespace {
 
@@ -905,7 +907,8 @@ namespace mmd {
 namespace {
 int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
                      int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
-                     uint32_t* thr_local, void* const* thr_all_host, int n_thr, const PairOut* po, void* stream) {
+                     uint32_t* thr_local, void* const* thr_all_host, int n_thr, const PairOut* po, void* stream,
+                     const PeerArrive* arrive = nullptr) {
   MMD_REQUIRE(Q >= 0 && N >= 0 && dim > 0 && k > 0, "mmd_topk_scores: Q=%lld N=%lld dim=%d k=%d", (long long)Q,
               (long long)N, dim, k);
   MMD_REQUIRE(N < (1ll << 31) && Q < (1ll << 31), "mmd_topk_scores: Q and N must be < 2^31");
@@ -919,7 +922,7 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   MMD_REQUIRE(cap != 0, "mmd_topk_scores: k=%d exceeds the fused selection limit %d", k, mmd_topk_max_k());
   if (N == 0) {
     // empty corpus: every slot is (-inf, -1)
-    return merge_partial_keys(nullptr, 0, Q, k, k, 1.0f, idx_offset, out_scores, out_idx, st, po);
+    return merge_partial_keys(nullptr, 0, Q, k, k, 1.0f, idx_offset, out_scores, out_idx, st, po, arrive);
   }
   MMD_REQUIRE(q_prep != nullptr && c_prep != nullptr, "mmd_topk_scores: null operand");
   MMD_REQUIRE(reinterpret_cast<uintptr_t>(q_prep) % 16 == 0 && reinterpret_cast<uintptr_t>(c_prep) % 16 == 0,
@@ -992,7 +995,7 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   if (rc != MMD_OK) return rc;
 
   const float scale = f8 ? (1.0f / 65536.0f) : 1.0f;
-  return merge_partial_keys(p.partial, sch.S, Q, k, k, scale, idx_offset, out_scores, out_idx, st, po);
+  return merge_partial_keys(p.partial, sch.S, Q, k, k, scale, idx_offset, out_scores, out_idx, st, po, arrive);
 }
 }  // namespace
 }  // namespace mmd
@@ -1026,6 +1029,39 @@ extern "C" int mmd_topk_scores_shared(const void* q_prep, const void* c_prep, in
                 "mmd_topk_scores_shared: threshold array %d is null or misaligned", i);
   return topk_scores_impl(q_prep, c_prep, op_dtype, Q, N, dim, k, idx_offset, out_scores, out_idx, workspace,
                           workspace_bytes, thr_local, thr_all_host, n_thr, n_pair_dst > 0 ? &po : nullptr, stream);
+}
+
+extern "C" int mmd_sharded_candidates(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim, int k,
+                                      int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
+                                      size_t workspace_bytes, uint32_t* thr_local, void* const* thr_all_host, int n_thr,
+                                      int reset_thr, void* const* pair_dst_host, int n_pair_dst, int64_t pair_offset, int pair_width,
+                                      void* const* arrive_flags_host, int n_arrive, uint32_t* sync_state, void* stream) {
+  using namespace mmd;
+  const char* who = "mmd_sharded_candidates";
+  MMD_REQUIRE(n_pair_dst >= 1 && n_pair_dst <= 16 && pair_dst_host != nullptr && pair_offset >= 0 && pair_width >= k,
+              "%s: n_pair_dst=%d (1..16) pair_width=%d (>= k=%d)", who, n_pair_dst, pair_width, k);
+  PairOut po{};
+  po.n = n_pair_dst;
+  po.offset = pair_offset;
+  po.width = pair_width;
+  for (int i = 0; i < n_pair_dst; ++i) {
+    MMD_REQUIRE(pair_dst_host[i] != nullptr && reinterpret_cast<uintptr_t>(pair_dst_host[i]) % 8 == 0,
+                "%s: pair destination %d is null or not 8-byte aligned", who, i);
+    po.dst[i] = static_cast<int2*>(pair_dst_host[i]);
+  }
+  // n_thr = 0: thresholds private to this launch (kept in the workspace); else shared with the peers as in mmd_topk_scores_shared
+  MMD_REQUIRE(n_thr >= 0 && n_thr <= 8 && (n_thr == 0 || (thr_local != nullptr && thr_all_host != nullptr)),
+              "%s: thr_local / thr_all_host null or n_thr=%d not in 0..8", who, n_thr);
+  for (int i = 0; i < n_thr; ++i)
+    MMD_REQUIRE(thr_all_host[i] != nullptr && reinterpret_cast<uintptr_t>(thr_all_host[i]) % 4 == 0,
+                "%s: threshold array %d is null or misaligned", who, i);
+  PeerArrive arrive{};
+  int rc = fill_arrive(&arrive, arrive_flags_host, n_arrive, sync_state, who);
+  if (rc != MMD_OK) return rc;
+  if (n_thr > 0 && reset_thr != 0 && Q > 0)
+    MMD_CUDA_OK(cudaMemsetAsync(thr_local, 0, static_cast<size_t>(Q) * sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
+  return topk_scores_impl(q_prep, c_prep, op_dtype, Q, N, dim, k, idx_offset, out_scores, out_idx, workspace, workspace_bytes,
+                          n_thr > 0 ? thr_local : nullptr, thr_all_host, n_thr, &po, stream, n_arrive > 0 ? &arrive : nullptr);
 }
 
 extern "C" int mmd_scores_dense(const void* q_prep, const void* c_prep, int op_dtype, int64_t Q, int64_t N, int dim,

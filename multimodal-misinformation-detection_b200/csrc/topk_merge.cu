@@ -13,14 +13,15 @@
 // per 256-thread block, bitonic sort in shared memory (<= 4096 candidates).
 // Order: (score descending, row ascending).
 #include "common.cuh"
+#include "peer_sync.cuh"
+#include "warp_sort.cuh"
 
 namespace mmd {
 namespace {
 
-constexpr uint32_t kFull = 0xffffffffu;
-
 struct MergeSrc {
   PairOut po;             // optional packed copies of the result (see PairOut)
+  PeerArrive arrive;      // optional: signal every rank once the whole grid has stored its lists (row-sharded path)
   const uint64_t* keys;   // [Q][parts * k_in]                    (keys != nullptr)
   const int2* pairs;      // [parts][Q][k_in] {score bits, row}    (keys == nullptr, pairs != nullptr)
   const float* scores;    // [parts][Q][k_in]                      (otherwise)
@@ -43,94 +44,28 @@ __device__ __forceinline__ uint64_t load_candidate(const MergeSrc& s, int64_t q,
   return r < 0 ? 0ull : make_key(s.scores[off], static_cast<uint32_t>(r));
 }
 
-__device__ __forceinline__ void store_result(uint64_t key, float scale, int64_t idx_offset, float* out_s,
-                                             int32_t* out_i, const PairOut& po = PairOut{}, int64_t pos = 0) {
+// Entry i of query q's merged list: to out_s/out_i [Q, k_out] when i < k_out, and -- row-sharded corpora -- packed, straight
+// into every rank's gather buffer at pair q * width + i for i < width (entries beyond k_out are empties there).
+__device__ __forceinline__ void store_result(uint64_t key, float scale, int64_t idx_offset, float* out_s, int32_t* out_i,
+                                             int64_t q, int i, int k_out, const PairOut& po) {
+  if (i >= k_out) key = 0ull;
   const float sc = key == 0ull ? __int_as_float(0xff800000) : key_score(key) * scale;
   const int32_t ix = key == 0ull ? -1 : static_cast<int32_t>(static_cast<int64_t>(key_row(key)) + idx_offset);
-  *out_s = sc;
-  *out_i = ix;
-  // row-sharded corpora: the merged list also goes, packed, straight into every rank's gather buffer
-  const int2 v = make_int2(__float_as_int(sc), ix);
-  for (int d = 0; d < po.n; ++d) po.dst[d][po.offset + pos] = v;
-}
-
-template <int E>
-__device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[E], int lane) {
-#pragma unroll
-  for (int size = 2; size <= 32 * E; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 32) {
-        const int es = stride >> 5;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if ((e & es) == 0) {
-            const bool desc = ((e * 32 + lane) & size) == 0;
-            const uint64_t a = k[e], b = k[e | es];
-            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
-            k[e] = desc ? mx : mn;
-            k[e | es] = desc ? mn : mx;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const uint64_t other = __shfl_xor_sync(kFull, k[e], stride);
-          const bool lower = (lane & stride) == 0;
-          const bool desc = ((e * 32 + lane) & size) == 0;
-          const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
-          k[e] = (lower == desc) ? mx : mn;
-        }
-      }
+  if (i < k_out) {
+    out_s[q * k_out + i] = sc;
+    out_i[q * k_out + i] = ix;
+  }
+  if (po.n > 0) {
+    const int width = po.width > 0 ? po.width : k_out;
+    if (i < width) {
+      const int2 v = make_int2(__float_as_int(sc), ix);
+      const int64_t pos = po.offset + q * width + i;
+      for (int d = 0; d < po.n; ++d) po.dst[d][pos] = v;
     }
   }
 }
-
-template <int E>
-__global__ void __launch_bounds__(128)
-merge_warp_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, float* __restrict__ out_s,
-                  int32_t* __restrict__ out_i) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
-  if (q >= src.Q) return;
-  uint64_t k[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) k[e] = load_candidate(src, q, e * 32 + lane);
-  warp_bitonic_desc<E>(k, lane);
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = e * 32 + lane;
-    if (i < k_out) store_result(k[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
-  }
-  // k_out beyond the candidate count: empty slots
-  for (int i = 32 * E + lane; i < k_out; i += 32) store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i);
-}
-
-// Bitonic merge network: `k` holds a bitonic sequence over i = e * 32 + lane; afterwards it is descending in i.
-template <int E>
-__device__ __forceinline__ void warp_bitonic_merge_desc(uint64_t (&k)[E], int lane) {
-#pragma unroll
-  for (int stride = 16 * E; stride > 0; stride >>= 1) {
-    if (stride >= 32) {
-      const int es = stride >> 5;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        if ((e & es) == 0) {
-          const uint64_t a = k[e], b = k[e | es];
-          k[e] = a > b ? a : b;
-          k[e | es] = a > b ? b : a;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const uint64_t other = __shfl_xor_sync(kFull, k[e], stride);
-        const bool lower = (lane & stride) == 0;
-        const uint64_t mx = k[e] > other ? k[e] : other, mn = k[e] > other ? other : k[e];
-        k[e] = lower ? mx : mn;
-      }
-    }
-  }
+__device__ __forceinline__ int store_extent(int k_out, const PairOut& po) {
+  return (po.n > 0 && po.width > k_out) ? po.width : k_out;
 }
 
 // Streaming merge, one query per warp, lists of at most L = 32 * E entries.
@@ -143,7 +78,7 @@ merge_stream_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, fl
   constexpr int L = 32 * E;
   const int lane = threadIdx.x & 31;
   const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
-  if (q >= src.Q) return;
+  if (q < src.Q) {
   uint64_t best[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = 0ull;
@@ -165,19 +100,18 @@ merge_stream_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, fl
       }
       warp_bitonic_desc<E>(tmp, lane);
 #pragma unroll
-      for (int e = 0; e < E; ++e) nw[e] = __shfl_sync(kFull, tmp[E - 1 - e], 31 - lane);
+      for (int e = 0; e < E; ++e) nw[e] = __shfl_sync(kWarpFull, tmp[E - 1 - e], 31 - lane);
     }
 #pragma unroll
     for (int e = 0; e < E; ++e) best[e] = best[e] > nw[e] ? best[e] : nw[e];
     warp_bitonic_merge_desc<E>(best, lane);
   }
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = e * 32 + lane;
-    if (i < k_out) store_result(best[e], scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
+  for (int e = 0; e < E; ++e) store_result(best[e], scale, idx_offset, out_s, out_i, q, e * 32 + lane, k_out, src.po);
+  const int extent = store_extent(k_out, src.po);
+  for (int i = L + lane; i < extent; i += 32) store_result(0ull, scale, idx_offset, out_s, out_i, q, i, k_out, src.po);
   }
-  for (int i = L + lane; i < k_out; i += 32)
-    store_result(0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
+  peer_arrive_all(src.arrive);
 }
 
 template <int L>
@@ -200,8 +134,10 @@ merge_block_kernel(MergeSrc src, int k_out, float scale, int64_t idx_offset, flo
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < k_out; i += 256)
-    store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s + q * k_out + i, out_i + q * k_out + i, src.po, q * k_out + i);
+  const int extent = store_extent(k_out, src.po);
+  for (int i = threadIdx.x; i < extent; i += 256)
+    store_result(i < L ? keys[i] : 0ull, scale, idx_offset, out_s, out_i, q, i, k_out, src.po);
+  peer_arrive_all(src.arrive);
 }
 
 template <bool kSortedParts>
@@ -230,9 +166,11 @@ int launch_merge(const MergeSrc& src, int k_out, float scale, int64_t idx_offset
 }  // namespace
 
 int merge_partial_keys(const uint64_t* partial, int parts, int64_t Q, int k_in, int k_out, float scale,
-                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream, const PairOut* po) {
+                       int64_t idx_offset, float* out_scores, int32_t* out_idx, cudaStream_t stream, const PairOut* po,
+                       const PeerArrive* arrive) {
   MergeSrc src{};
   if (po != nullptr) src.po = *po;
+  if (arrive != nullptr) src.arrive = *arrive;
   src.keys = partial;
   src.pairs = nullptr;
   src.scores = nullptr;

@@ -52,9 +52,26 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                     C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_rescore_joint_pairs": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                          C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p]),
+    "mmd_sharded_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
+                                         C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                         C.c_void_p, C.c_void_p]),
+    "mmd_exchange_rescore": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                       C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.c_int,
+                                       C.c_int, C.c_int64, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "mmd_exchange_finish": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
     "mmd_dedupe_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "mmd_launch_count": (C.c_int64, []),
+    "mmd_build_info": (C.c_char_p, []),
     "mmd_profile_enable": (C.c_int, [C.c_int]),
     "mmd_profile_collect": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
 }
@@ -83,13 +100,19 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not LIB_PATH.exists():
-            if os.environ.get("MMD_NO_AUTOBUILD"):
-                raise MmdError(f"{LIB_PATH} is missing and MMD_NO_AUTOBUILD is set; there is no CPU fallback")
+        if os.environ.get("MMD_LIB_PATH") or os.environ.get("MMD_NO_AUTOBUILD"):
+            if not LIB_PATH.exists():
+                raise MmdError(f"{LIB_PATH} is missing and auto-build is off; there is no CPU fallback")
+        else:
+            # build_lib() is a no-op when the recorded source hash matches; it rebuilds a missing OR stale library
+            # (one builder at a time under a file lock: every rank of a torchrun job lands here at once)
             try:
                 _try_build()
             except Exception as e:  # noqa: BLE001
-                raise MmdError(f"{LIB_PATH} is missing and building it failed ({e}); there is no CPU fallback") from e
+                if not LIB_PATH.exists():
+                    raise MmdError(f"{LIB_PATH} is missing and building it failed ({e}); there is no CPU fallback") from e
+                import warnings
+                warnings.warn(f"libmmd.so may be stale: rebuilding failed ({e})")
         lib = C.CDLL(str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here = header and library disagree
@@ -99,6 +122,11 @@ def load():
             raise MmdError(f"libmmd ABI version {lib.mmd_abi_version()} != 1")
         _lib = lib
         return _lib
+
+
+def build_info() -> str:
+    """Provenance string compiled into the loaded binary (source hash, nvcc version, arch)."""
+    return load().mmd_build_info().decode("utf-8", "replace")
 
 
 def last_error() -> str:

@@ -55,15 +55,22 @@ def _segment_layout(op: str, dims: Sequence[int]) -> Tuple[List[int], int]:
 
 
 def _cast_segments(mats: Sequence[torch.Tensor], op: str, side: int, normalize: bool, eps: float, scales: Sequence[float],
-                   seg_bytes: Sequence[int], row_bytes: int):
+                   seg_bytes: Sequence[int], row_bytes: int, out=None):
+    """out = (rows buffer uint8 [>= rows, row_bytes], [inv_norm buffer f32 [>= rows] per modality]): caller-owned
+    destinations, no allocation."""
     rows = mats[0].shape[0]
     dev = mats[0].device
-    out = torch.empty((rows, row_bytes), dtype=torch.uint8, device=dev)
+    inv_bufs = None
+    if out is None:
+        out = torch.empty((rows, row_bytes), dtype=torch.uint8, device=dev)
+    else:
+        out, inv_bufs = out
+        assert out.shape[1] == row_bytes and out.shape[0] >= rows and out.is_contiguous()
     invs = []
     lib = _lib.load()
     off = 0
-    for x, sb, sc in zip(mats, seg_bytes, scales):
-        inv = torch.empty((rows,), dtype=torch.float32, device=dev)
+    for m, (x, sb, sc) in enumerate(zip(mats, seg_bytes, scales)):
+        inv = torch.empty((rows,), dtype=torch.float32, device=dev) if inv_bufs is None else inv_bufs[m]
         if rows:
             with torch.cuda.device(dev):
                 rc = lib.mmd_normalize_cast_segment(ops._ptr(x), ops._SRC_DTYPE[x.dtype], rows, x.shape[1], x.stride(0), int(normalize),

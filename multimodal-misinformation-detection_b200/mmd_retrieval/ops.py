@@ -73,13 +73,20 @@ def prepared_layout(op: str, dim: int) -> Tuple[int, int]:
     return kdim.value, row_bytes.value
 
 
-def normalize_cast(x: torch.Tensor, op: str, side: int, normalize: bool, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    """K1: rows of `x` -> (prepared operand rows uint8 [rows, row_bytes], inv_norm f32 [rows])."""
+def normalize_cast(x: torch.Tensor, op: str, side: int, normalize: bool, eps: float,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1: rows of `x` -> (prepared operand rows uint8 [rows, row_bytes], inv_norm f32 [rows]).
+    out = (rows buffer, inv_norm buffer): caller-owned destinations (first `rows` rows are written), no allocation."""
     _require_cuda(x.device)
     rows, dim = x.shape
     _, row_bytes = prepared_layout(op, dim)
-    out = torch.empty((rows, row_bytes), dtype=torch.uint8, device=x.device)
-    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((rows, row_bytes), dtype=torch.uint8, device=x.device)
+        inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    else:
+        out, inv = out
+        assert out.dtype == torch.uint8 and out.shape[0] >= rows and out.shape[1] == row_bytes and out.is_contiguous()
+        assert inv.dtype == torch.float32 and inv.shape[0] >= rows
     if rows:
         lib = _lib.load()
         with torch.cuda.device(x.device):
@@ -431,6 +438,65 @@ def scatter_pairs(scores: torch.Tensor, idx: torch.Tensor, dst_ptrs: Sequence[in
         rc = _lib.load().mmd_scatter_pairs(_ptr(scores), _ptr(idx), n_queries, k, arr, len(dst_ptrs), int(dst_offset_pairs),
                                            _stream_ptr(scores.device))
     _lib.check(rc, "mmd_scatter_pairs")
+
+
+# ---------------------------------------------------------------------------------------------- row-sharded step, stage by stage
+def _vp(ptrs: Sequence[int]):
+    return (C.c_void_p * max(len(ptrs), 1))(*[C.c_void_p(int(p)) for p in ptrs])
+
+
+def sharded_candidates(q_rows: torch.Tensor, n_queries: int, corpus, k_loc: int, raw_s: torch.Tensor, raw_i: torch.Tensor,
+                       ws: torch.Tensor, thr_all: Sequence[int], own: int, share_thr: bool, gather_ptrs: Sequence[int],
+                       pair_offset: int, pair_width: int, arrive_ptrs: Sequence[int] = (), sync_ptr: int = 0) -> None:
+    """Stage C of a sharded step (mmd_sharded_candidates) on the current stream: fused top-k_loc over this rank's shard; the
+    strip merge stores the list, padded to pair_width, at pair pair_offset + q * pair_width into every gather buffer and
+    raises the arrive flags.  corpus: PreparedCorpus or JointCorpus (rows / op / n / dim / idx_offset are used)."""
+    dev = corpus.device
+    with torch.cuda.device(dev):
+        rc = _lib.load().mmd_sharded_candidates(
+            _ptr(q_rows), C.c_void_p(corpus.rows.data_ptr() if corpus.n else 0), _OP_DTYPE[corpus.op], n_queries, corpus.n, corpus.dim,
+            k_loc, corpus.idx_offset, _ptr(raw_s), _ptr(raw_i), _ptr(ws), ws.numel(),
+            C.c_void_p(int(thr_all[own]) if thr_all else 0), _vp(thr_all), len(thr_all) if share_thr else 0, 1,
+            _vp(gather_ptrs), len(gather_ptrs), int(pair_offset), int(pair_width),
+            _vp(arrive_ptrs), len(arrive_ptrs), C.c_void_p(int(sync_ptr)), _stream_ptr(dev))
+    _lib.check(rc, "mmd_sharded_candidates")
+
+
+def segment_tables(q_mats: Sequence[torch.Tensor], row0: int, q_invs: Sequence[Optional[torch.Tensor]], c_srcs: Sequence[torch.Tensor],
+                   c_invs: Sequence[Optional[torch.Tensor]], dims: Sequence[int], weights: Sequence[float]):
+    """ctypes tables of the multi-modality re-score (argument block shared by mmd_rescore_joint and mmd_exchange_rescore) for
+    the query rows starting at row0."""
+    n_seg = len(dims)
+    vp, ip, lp, fp = C.c_void_p * n_seg, C.c_int * n_seg, C.c_int64 * n_seg, C.c_float * n_seg
+    return (n_seg,
+            vp(*[C.c_void_p(m.data_ptr() + row0 * m.stride(0) * m.element_size()) for m in q_mats]),
+            ip(*[_SRC_DTYPE[m.dtype] for m in q_mats]), lp(*[m.stride(0) for m in q_mats]),
+            vp(*[C.c_void_p(0 if t is None else t.data_ptr()) for t in q_invs]),
+            vp(*[C.c_void_p(s.data_ptr() if s.shape[0] else 0) for s in c_srcs]),
+            ip(*[_SRC_DTYPE[s.dtype] for s in c_srcs]), lp(*[s.stride(0) if s.shape[0] else d for s, d in zip(c_srcs, dims)]),
+            vp(*[C.c_void_p(0 if t is None else t.data_ptr()) for t in c_invs]), ip(*dims), fp(*weights))
+
+
+def exchange_rescore(gather_ptr: int, parts: int, part_stride: int, n_queries: int, k_in: int, kc: int, tables, n_local: int,
+                     idx_offset: int, resc_ptrs: Sequence[int], own: int, device: torch.device, wait_ptr: int = 0, n_wait: int = 0,
+                     arrive_ptrs: Sequence[int] = (), sync_ptr: int = 0) -> None:
+    """Stage X (mmd_exchange_rescore) on the current stream."""
+    with torch.cuda.device(device):
+        rc = _lib.load().mmd_exchange_rescore(
+            C.c_void_p(int(gather_ptr)), parts, int(part_stride), n_queries, k_in, kc, *tables, n_local, idx_offset,
+            _vp(resc_ptrs), len(resc_ptrs), own, 0, C.c_void_p(int(wait_ptr)), n_wait, _vp(arrive_ptrs), len(arrive_ptrs),
+            C.c_void_p(int(sync_ptr)), _stream_ptr(device))
+    _lib.check(rc, "mmd_exchange_rescore")
+
+
+def exchange_finish(resc_ptr: int, n_queries: int, kc: int, k_out: int, out_s_ptr: int, out_i_ptr: int, idx64: bool,
+                    device: torch.device, wait_ptr: int = 0, n_wait: int = 0, sync_ptr: int = 0) -> None:
+    """Stage F (mmd_exchange_finish) on the current stream: out_s f32 [Q,k_out], out_i i64 / i32 [Q,k_out] at the given pointers."""
+    with torch.cuda.device(device):
+        rc = _lib.load().mmd_exchange_finish(C.c_void_p(int(resc_ptr)), n_queries, kc, k_out, C.c_void_p(int(out_s_ptr)),
+                                             C.c_void_p(int(out_i_ptr)), int(idx64), C.c_void_p(int(wait_ptr)), n_wait,
+                                             C.c_void_p(int(sync_ptr)), _stream_ptr(device))
+    _lib.check(rc, "mmd_exchange_finish")
 
 
 def dedupe_scores(scores: torch.Tensor, idx: torch.Tensor, top_k: int, gold_idx: Optional[torch.Tensor] = None

@@ -1,34 +1,53 @@
 """Row-sharded corpus across the GPUs of one box.
 
-One process per GPU (torchrun).  The corpus rows are split contiguously over the ranks; queries are
-replicated; every rank runs the fused top-K on its shard and emits (score f32, GLOBAL row i32) lists; one
-exchange of Q*K*8 bytes per rank and a `world`-way merge on the device (K4) give every rank the global top-K.
-Scoring never crosses GPUs; the exchange is the path's only communication step.  Two implementations:
+One process per GPU (torchrun).  The corpus rows are split contiguously over the ranks; queries are replicated; every
+rank runs the fused tensor-core top-K' on its shard; the ranks' candidate lists are exchanged, merged, re-scored exactly
+and merged again.  Scoring never crosses GPUs.  The reference has no counterpart (single process, single device): the step
+stands where sentence_transformers.util.semantic_search folds its corpus chunks together with a per-query heap (call
+sites src/evidence/text2text_retrieval.py:56-64, src/evidence/experiment_text.py:25-33).
 
-  exchange="peer"  the re-score kernel (K5) stores each rank's list directly into EVERY rank's gather buffer
-                   (peer-mapped symmetric memory, the stores travel over NVLink 5 / NVSwitch while the kernel
-                   is still scoring other queries); one signal-pad barrier follows.  No collective launch.
-  exchange="nccl"  K5 fills a local send buffer, one `all_gather_into_tensor` moves it.
+exchange="peer" (default when symmetric memory comes up on every rank): ONE search step is three kernels-with-flags per
+rank and NO collective or barrier launch (csrc/exchange.cu, csrc/peer_sync.cuh):
 
-"auto" (default) uses "peer" when symmetric memory can be set up on every rank, else "nccl".
+  stage C   K1 on the queries -> fused tcgen05 score + top-K' over the shard (pruning thresholds shared by all GPUs through
+            system-scope atomics) -> strip merge, which stores this rank's raw candidate list into EVERY rank's gather buffer
+            over NVLink and raises flag set 1;
+  stage X   wait for flag set 1 -> merge the `world` candidate lists (same result on every rank) -> exact fp32 re-score of
+            the global candidates that live in THIS shard (K'/world per query on average) -> store each at its position in
+            every rank's re-score buffer -> raise flag set 2;
+  stage F   wait for flag set 2 -> sort the K' exact keys per query -> final top-k (int64 rows, no conversion kernel).
 
-Order of the stages (`rescore="global"`, the default): the tensor-core pass over-fetches K' candidates per shard; the
-K' raw lists are exchanged and merged FIRST, and only the global K' candidates are re-scored exactly -- each rank
-re-scores the candidates that live in its own shard (K'/world per query on average instead of K') and a second, smaller
-exchange + merge gives the final list.  `rescore="local"` re-scores every shard's K' candidates before a single exchange.
-`ShardedCorpus.capture()` records the whole step (all kernels and the exchange) in a CUDA graph for replay.
-The reference has no counterpart (single process, single device).
+The step is PIPELINED: stage C runs on one stream, stages X and F on another, and a query batch is cut into sub-batches,
+so the exchange/re-score tail of sub-batch i hides under the contraction of sub-batch i+1 (the tail -- ~0.3 ms of small
+kernels at 8 GPUs -- was what bounded the 8-GPU efficiency of round 1).  All cross-GPU buffers form a ring of three slots;
+why three, and why no barrier is needed:
 
-`local_topk` / `merge` are injectable so the partition / offset / gather plumbing can be exercised with
-gloo on CPU (tests/test_sharded_gloo.py injects the CPU oracle there -- the product path below uses the
-CUDA ops and nothing else).
+  * stage C of step s starts only after THIS rank's stage F of step s-2 has finished.  F(s-2) waited for flag set 2 of
+    step s-2 from every rank; a rank raises it at the end of its X(s-2), which runs (in-order stream) after its F(s-3).
+    So when any rank begins to store step s's candidates into slot s % 3, every rank has finished reading slot (s-3) % 3.
+  * the shared threshold array of a slot is reset at the start of stage C (a memset in front of the contraction).  Peers
+    publish into it only during their own stage C of the same step (same queries => valid bounds); bounds that land before
+    the reset are lost, which only weakens the pruning; bounds of step s-3 cannot arrive late because this rank passed
+    flag set 1 of step s-3 long ago.  Every step resets exactly the entries it is about to read, so a smaller batch
+    after a larger one never sees the larger one's bounds.
+
+`topk()` waits for the last sub-batch before returning; `topk_stream()` also overlaps successive batches, including the
+host->device upload of the next batch and the device->host read of the previous one.
+
+exchange="nccl" (or rescore="local"): the plain variant -- per-rank lists, one `all_gather_into_tensor`, K4 merge.
+`local_topk` / `merge` are injectable so the partition / offset / gather plumbing can be exercised with gloo on CPU
+(tests/test_sharded_gloo.py injects the CPU oracle there -- the product path uses the CUDA ops and nothing else).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import ctypes as C
+from collections import deque
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+RING = 3          # slots of cross-GPU buffers (see module docstring)
 
 
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
@@ -39,7 +58,9 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def _cuda_local_topk(queries, shard, k):
-    from . import ops
+    from . import joint, ops
+    if isinstance(shard, joint.JointCorpus):
+        return joint.topk_joint(queries, shard, k, index_dtype=torch.int32)
     return ops.topk(queries, shard, k, index_dtype=torch.int32)
 
 
@@ -48,71 +69,106 @@ def _cuda_merge(scores, idx, k):
     return ops.merge_topk(scores, idx, k)
 
 
-class _PeerExchange:
-    """Double-buffered gather buffers [2][world][cap pairs] in symmetric (peer-mapped) memory.
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
 
-    Step i uses buffer i % 2 of every rank; every exchange inside a step is "store to all peers, then ONE signal-pad
-    barrier".  Reuse without a barrier in front of the stores is safe: a rank passes the first barrier of step i only
-    after every peer has finished its own stores of step i, which in stream order come after that peer's last read of
-    step i-1 -- and the buffer written in step i+1 was last read in step i-1."""
 
-    def __init__(self, group, world: int, cap_pairs: int, q_cap: int, device: torch.device):
+class _PeerRing:
+    """Symmetric (peer-mapped) memory of the sharded step: RING slots of {gather buffer [world][q_cap x kp] pairs, re-score
+    buffer [q_cap x kc] pairs, threshold array [q_cap]} plus two flag arrays [world], carved out of ONE allocation; local
+    sync words and scratch (prepared queries, raw lists, workspace) per slot."""
+
+    def __init__(self, group, world: int, rank: int, q_cap: int, kp: int, kc: int, row_bytes: int, n_seg: int,
+                 device: torch.device):
         import torch.distributed._symmetric_memory as symm_mem
         grp = group if group is not None else dist.group.WORLD
-        self.world, self.cap, self.q_cap = world, cap_pairs, q_cap
-        self.buf = symm_mem.empty((2, world, cap_pairs, 2), dtype=torch.int32, device=device)
+        self.world, self.rank, self.q_cap, self.kp, self.kc = world, rank, q_cap, kp, kc
+        self.row_bytes, self.n_seg, self.ws_bytes = row_bytes, n_seg, 0
+        self.device = device
+        self.gather_bytes = _align(world * q_cap * kp * 8)
+        self.resc_bytes = _align(q_cap * kc * 8)
+        self.thr_bytes = _align(q_cap * 4)
+        self.off_gather = 0
+        self.off_resc = self.off_gather + RING * self.gather_bytes
+        self.off_thr = self.off_resc + RING * self.resc_bytes
+        self.off_flags = self.off_thr + RING * self.thr_bytes
+        total = self.off_flags + 2 * 256
+        self.buf = symm_mem.empty((total,), dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, grp)
-        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        # per-query pruning thresholds shared by all ranks (one array per step parity), see mmd_topk_scores_shared
-        self.thr = symm_mem.empty((2, q_cap), dtype=torch.int32, device=device)
-        self.thr_hdl = symm_mem.rendezvous(self.thr, grp)
-        self.thr_ptrs = [int(p) for p in self.thr_hdl.buffer_ptrs]
-        self.thr.zero_()
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                                  # every rank's flags are zero before anyone raises one
+        # local: sync words {launches, blocks done} of stages C, X, F (64 B apart) and per-slot scratch
+        self.sync = torch.zeros((48,), dtype=torch.int32, device=device)
+        self.q_rows = [torch.empty((q_cap, row_bytes), dtype=torch.uint8, device=device) for _ in range(RING)]
+        self.q_inv = [[torch.empty((q_cap,), dtype=torch.float32, device=device) for _ in range(n_seg)] for _ in range(RING)]
+        self.raw_s = [torch.empty((q_cap, kp), dtype=torch.float32, device=device) for _ in range(RING)]
+        self.raw_i = [torch.empty((q_cap, kp), dtype=torch.int32, device=device) for _ in range(RING)]
+        self.ws = [None] * RING                                    # fused-kernel workspace per slot, grown on demand (local)
+        self.ev_c = [torch.cuda.Event() for _ in range(RING)]
+        self.ev_f = [torch.cuda.Event() for _ in range(RING)]
         self.step = 0
-        self.hdl.barrier(channel=0)            # every rank's threshold arrays are zero before anyone publishes
+        torch.cuda.synchronize(device)
 
-    def thr_slot(self, parity: int):
-        """(this rank's threshold array of the given parity, every rank's) as device pointers."""
-        off = parity * self.q_cap * 4
-        return self.thr.data_ptr() + off, [p + off for p in self.thr_ptrs]
+    def fits(self, q_sub: int, kp: int, kc: int, row_bytes: int, n_seg: int) -> bool:
+        return q_sub <= self.q_cap and kp == self.kp and kc == self.kc and row_bytes == self.row_bytes and n_seg == self.n_seg
 
-    def slot(self, parity: Optional[int] = None):
-        """(peer base pointers of this step's buffer, local view [world, cap, 2] of it)."""
-        b = self.step % 2 if parity is None else parity
-        off_bytes = b * self.world * self.cap * 2 * 4
-        return [p + off_bytes for p in self.ptrs], self.buf[b]
+    def ensure_workspace(self, nbytes: int) -> None:
+        """Local scratch, no collective.  Growing it waits for the device first: nothing may still be using the old one."""
+        if nbytes > self.ws_bytes:
+            torch.cuda.synchronize(self.device)
+            self.ws = [torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=self.device) for _ in range(RING)]
+            self.ws_bytes = nbytes
 
-    def barrier(self):
-        self.hdl.barrier(channel=0)
+    # device pointers (ints)
+    def gather_all(self, slot):  # every rank's gather buffer of this slot
+        return [b + self.off_gather + slot * self.gather_bytes for b in self.base]
 
-    def next_step(self):
-        self.step += 1
+    def resc_all(self, slot):
+        return [b + self.off_resc + slot * self.resc_bytes for b in self.base]
+
+    def thr_all(self, slot):
+        return [b + self.off_thr + slot * self.thr_bytes for b in self.base]
+
+    def flags_local(self, which):
+        return self.base[self.rank] + self.off_flags + which * 256
+
+    def flags_arrive(self, which):  # this rank's word in every rank's flag array
+        return [b + self.off_flags + which * 256 + self.rank * 4 for b in self.base]
+
+    def sync_ptr(self, stage):
+        return self.sync.data_ptr() + stage * 64
 
 
 class ShardedCorpus:
-    """This rank's shard of a row-sharded corpus plus the collective that merges local top-K lists."""
+    """This rank's shard of a row-sharded corpus plus the exchange that merges the ranks' lists."""
 
     def __init__(self, local_rows, n_total: int, start: int, group=None, dtype: str = "bf16", metric: str = "cos",
                  eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: str = "global", share_thresholds: bool = True,
-                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None, prepare: Optional[Callable] = None,
-                 _shard=None):
+                 sub_batches: int = 0, local_topk: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 prepare: Optional[Callable] = None, _shard=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = int(n_total)
         self.start = int(start)
         self._max_local = -(-self.n_total // self.world)           # rows of the largest shard (balanced contiguous split)
+        self._min_local = self.n_total // self.world
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         if rescore not in ("global", "local"):
             raise ValueError("rescore must be 'global' or 'local'")
         self.rescore = rescore
         self.share_thresholds = share_thresholds
+        self.sub_batches = int(sub_batches)   # 0 = auto
         self.phases = 1                   # single-GPU searches: launches per sweep of the shard (ops.topk_prepared_phased)
         self._exchange_req = exchange
         self.exchange = "nccl"            # what is actually in use; "peer" once symmetric memory is up on every rank
-        self._peer: Optional[_PeerExchange] = None
+        self._ring: Optional[_PeerRing] = None            # the ring of the call in progress
+        self._rings = {}                                  # (kp, kc, row_bytes, n_seg) -> ring (one per list geometry, grown on demand)
         self._peer_failed = False
+        self._streams = None
         self._injected = local_topk is not None or merge is not None or prepare is not None
         self._local_topk = local_topk or _cuda_local_topk
         self._merge = merge or _cuda_merge
@@ -128,6 +184,7 @@ class ShardedCorpus:
             self.shard = prepare(local_rows, self.start)
             self.n_local = int(local_rows.shape[0]) if hasattr(local_rows, "shape") else int(local_rows[0].shape[0])
 
+    # ------------------------------------------------------------------------------------------ constructors
     @classmethod
     def from_full(cls, corpus: torch.Tensor, group=None, **kw) -> "ShardedCorpus":
         """Every rank passes the same full corpus (or a view of it); each keeps only its own rows."""
@@ -137,162 +194,227 @@ class ShardedCorpus:
         return cls(corpus[lo:hi], corpus.shape[0], lo, group=group, **kw)
 
     @classmethod
-    def from_prepared(cls, shard, n_total: int, group=None, exchange: str = "auto", rescore: str = "global") -> "ShardedCorpus":
-        """Wrap this rank's already prepared shard (e.g. corpus_io.prepare_streamed(..., idx_offset=start))."""
-        return cls(None, n_total, shard.idx_offset, group=group, exchange=exchange, rescore=rescore, _shard=shard)
+    def from_prepared(cls, shard, n_total: int, group=None, **kw) -> "ShardedCorpus":
+        """Wrap this rank's already prepared shard (e.g. corpus_io.prepare_streamed(..., idx_offset=start)), a PreparedCorpus
+        or a JointCorpus."""
+        return cls(None, n_total, shard.idx_offset, group=group, _shard=shard, **kw)
 
     @classmethod
     def from_joint(cls, local_corpora, n_total: int, start: int, weights=None, group=None, dtype: str = "bf16",
-                   metric: str = "cos", eps: float = 1e-12) -> "ShardedCorpus":
+                   metric: str = "cos", eps: float = 1e-12, **kw) -> "ShardedCorpus":
         """Row-sharded JOINT (multi-modality) corpus: local_corpora = this rank's rows of every modality; queries are
-        passed to topk() as a list with one matrix per modality."""
-        from . import joint, ops
+        passed to topk() as a list with one matrix per modality.  Same exchange as the single-modality corpus."""
+        from . import joint
+        jc = joint.prepare_joint(local_corpora, weights, dtype=dtype, metric=metric, eps=eps, idx_offset=start)
+        return cls(None, n_total, start, group=group, _shard=jc, **kw)
 
-        def prepare(rows, first):
-            return joint.prepare_joint(rows, weights, dtype=dtype, metric=metric, eps=eps, idx_offset=first)
+    # ------------------------------------------------------------------------------------------ helpers
+    @property
+    def _is_joint(self) -> bool:
+        from . import joint
+        return isinstance(self.shard, joint.JointCorpus)
 
-        def local_topk(queries, shard, k):
-            return joint.topk_joint(queries, shard, k, index_dtype=torch.int32)
+    def _has_source(self) -> bool:
+        return self.shard.source is not None
 
-        sc = cls(local_corpora, n_total, start, group=group, prepare=prepare, local_topk=local_topk,
-                 merge=lambda s, i, k: ops.merge_topk(s, i, k))
-        sc.n_local = sc.shard.n
-        return sc
+    def _query_mats(self, queries, device=None) -> List[torch.Tensor]:
+        """queries (one matrix, or one per modality for a joint corpus) -> list of 2-D row tensors."""
+        from . import ops
+        if self._is_joint:
+            if not isinstance(queries, (list, tuple)) or len(queries) != len(self.shard.dims):
+                raise ValueError(f"a joint corpus takes a list of {len(self.shard.dims)} query matrices (one per modality)")
+            mats = [ops._as_rows(q, device) for q in queries]
+            dims = self.shard.dims
+        else:
+            mats = [ops._as_rows(queries, device)]
+            dims = [self.shard.dim]
+        n = mats[0].shape[0]
+        for m, d in zip(mats, dims):
+            if m.shape[1] != d:
+                raise RuntimeError(f"query dim {m.shape[1]} does not match corpus dim {d}")
+            if m.shape[0] != n:
+                raise ValueError("every modality must have the same number of queries")
+        return mats
 
-    def topk(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Global top-k over all shards: (scores f32 [Q,k'], global rows i64 [Q,k']), k' = min(k, n_total)."""
-        if self._injected:
-            return self._topk_generic(queries, k)
+    def _pipe_streams(self):
+        if self._streams is None:
+            dev = self.shard.device
+            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))     # contraction, tail, h2d, d2h
+        return self._streams
+
+    def _widths(self, k: int) -> Tuple[int, int, int]:
+        """(k_glob, kp, kc): final list length, candidate-list width every rank exchanges, global candidate-list length."""
         from . import ops
         k_glob = min(k, self.n_total)
-        shard = self.shard
-        if self.world == 1:
-            return ops.topk(queries, shard, k, phases=self.phases)
-        if shard.source is None:
-            return self._topk_generic(queries, k)
-        dev = shard.device
-        q = self.upload_queries(queries)
-        n_queries = q.shape[0]
-        # every rank must exchange lists of one common width: the over-fetch of the LARGEST shard
-        kp_glob = ops.overfetch_for(min(k, self._max_local), self._max_local)
-        two_phase = self.rescore == "global"
-        cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
-        peer = self._peer_for(cap, n_queries, dev)
-        return self._search(q, k, k_glob, kp_glob, peer, two_phase, peer.step % 2 if peer is not None else 0, advance=True)
+        kp = ops.overfetch_for(min(k, self._max_local), self._max_local)
+        kc = min(self.world * kp, ops.overfetch_for(k_glob, self.n_total))
+        return k_glob, kp, kc
 
-    def upload_queries(self, queries, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Host-resident query batch (the SAME on every rank) -> device.  With more than one rank each rank uploads only its
-        1/world slice over PCIe and the slices are all-gathered over NVLink, instead of every rank pulling the whole batch
-        through the host's memory system: 8 x 50 MB per step at C3 otherwise.  Device tensors pass through."""
+    # ------------------------------------------------------------------------------------------ public search
+    def topk(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Global top-k over all shards: (scores f32 [Q,k'], global rows i64 [Q,k']), k' = min(k, n_total)."""
+        if k <= 0:
+            raise ValueError("k must be positive")
+        if self._injected:
+            return self._topk_generic(queries, k)
+        if self.world == 1:
+            return _cuda_local_topk_i64(queries, self.shard, k, self.phases)
+        if not self._has_source() or self.rescore == "local" or self._exchange_req == "nccl":
+            return self._topk_gather(queries, k)
+        dev = self.shard.device
+        mats = self.upload_queries(queries)
+        if not self._ring_for(mats[0].shape[0], k):
+            return self._topk_gather(mats if self._is_joint else mats[0], k)
+        s, i, done = self._run_pipelined(mats, k, None)
+        if done is not None:
+            torch.cuda.current_stream(dev).wait_event(done)
+        return s, i
+
+    def topk_stream(self, batches: Iterable, k: int, to_host: bool = False, depth: int = 2):
+        """Pipelined search over an iterable of query batches; yields (scores, rows) per batch, in order.
+
+        The host->device upload of batch i+1 (own stream), the search of batch i and -- with to_host=True -- the
+        device->host read of batch i-1 into pinned buffers (own stream) overlap; with several GPUs the exchange tail of a
+        batch also hides under the contraction of the next one.  Up to `depth` batches are in flight behind the one being
+        yielded.  to_host=False yields device tensors that are safe to use on the caller's current stream."""
+        if self._injected:
+            for b in batches:
+                yield self._topk_generic(b, k)
+            return
+        dev = self.shard.device
+        c_stream, t_stream, h2d, d2h = self._pipe_streams()
+        cur = torch.cuda.current_stream(dev)
+        pending = deque()
+        plain = self.world > 1 and (not self._has_source() or self.rescore == "local" or self._exchange_req == "nccl")
+
+        def finish(item):
+            s, i, done, ev_host, hs, hi, keep = item
+            if to_host:
+                ev_host.synchronize()
+                return hs, hi
+            if done is not None:
+                cur.wait_event(done)
+            s.record_stream(cur)
+            i.record_stream(cur)
+            return s, i
+
+        for b in batches:
+            ev_b = torch.cuda.Event()                              # the batch (if device-resident) is ready on the caller's stream
+            ev_b.record(cur)
+            h2d.wait_event(ev_b)
+            with torch.cuda.stream(h2d):
+                mats = self.upload_queries(b)
+                ev_up = torch.cuda.Event()
+                ev_up.record(h2d)
+            if self.world == 1 or plain or not self._ring_for(mats[0].shape[0], k):
+                with torch.cuda.stream(c_stream):
+                    c_stream.wait_event(ev_up)
+                    qq = mats if self._is_joint else mats[0]
+                    if self.world == 1:
+                        s, i = _cuda_local_topk_i64(qq, self.shard, k, self.phases)
+                    else:
+                        s, i = self._topk_gather(qq, k)
+                    done = torch.cuda.Event()
+                    done.record(c_stream)
+                for m in mats:
+                    m.record_stream(c_stream)
+            else:
+                s, i, done = self._run_pipelined(mats, k, ev_up)
+                for m in mats:
+                    m.record_stream(c_stream)
+                    m.record_stream(t_stream)
+            ev_host = hs = hi = None
+            if to_host:
+                with torch.cuda.stream(d2h):
+                    if done is not None:
+                        d2h.wait_event(done)
+                    hs = torch.empty(s.shape, dtype=s.dtype, pin_memory=True)
+                    hi = torch.empty(i.shape, dtype=i.dtype, pin_memory=True)
+                    hs.copy_(s, non_blocking=True)
+                    hi.copy_(i, non_blocking=True)
+                    ev_host = torch.cuda.Event()
+                    ev_host.record(d2h)
+                s.record_stream(d2h)
+                i.record_stream(d2h)
+            pending.append((s, i, done, ev_host, hs, hi, mats))
+            while len(pending) > depth:
+                yield finish(pending.popleft())
+        while pending:
+            yield finish(pending.popleft())
+
+    def upload_queries(self, queries, out: Optional[torch.Tensor] = None):
+        """Host-resident query batch (the SAME on every rank) -> list of device matrices (one per modality) on the current
+        stream.  With more than one rank each rank uploads only its 1/world slice over PCIe and the slices are all-gathered
+        over NVLink, instead of every rank pulling the whole batch through the host's memory system: 8 x 50 MB per step at
+        C3 otherwise.  Device tensors pass through.  `out` (single-modality only): static destination buffer."""
+        dev = self.shard.device
+        if self._is_joint and out is None and isinstance(queries, (list, tuple)):
+            return [self._upload_one(q, None) for q in self._query_mats(queries)]
+        mats = self._query_mats(queries)
+        return [self._upload_one(mats[0], out)]
+
+    def _upload_one(self, q, out):
         from . import ops
         dev = self.shard.device
-        if (isinstance(queries, torch.Tensor) and queries.is_cuda) or self.world == 1 or self._injected:
-            q = ops._as_rows(queries, dev)
+        if q.is_cuda or self.world == 1 or self._injected:
+            q = ops._as_rows(q, dev)
             if out is not None:
                 out.copy_(q, non_blocking=True)
                 return out
             return q
-        q_host = ops._as_rows(queries)
-        n_queries, dim = q_host.shape
+        n_queries, dim = q.shape
         per = -(-n_queries // self.world)
         lo = min(n_queries, self.rank * per)
         hi = min(n_queries, lo + per)
-        mine = torch.zeros((per, dim), dtype=q_host.dtype, device=dev) if hi - lo < per else \
-            torch.empty((per, dim), dtype=q_host.dtype, device=dev)
+        mine = torch.zeros((per, dim), dtype=q.dtype, device=dev) if hi - lo < per else \
+            torch.empty((per, dim), dtype=q.dtype, device=dev)
         if hi > lo:
-            mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
-        full = torch.empty((self.world * per, dim), dtype=q_host.dtype, device=dev)
+            mine[:hi - lo].copy_(q[lo:hi], non_blocking=True)
+        full = torch.empty((self.world * per, dim), dtype=q.dtype, device=dev)
         dist.all_gather_into_tensor(full, mine, group=self.group)
-        q = full[:n_queries]
+        res = full[:n_queries]
         if out is not None:
-            out.copy_(q, non_blocking=True)
+            out.copy_(res, non_blocking=True)
             return out
-        return q
+        return res
 
-    def _search(self, q, k, k_glob, kp_glob, peer, two_phase, parity, advance):
-        """One search step on the current stream (eager or under CUDA-graph capture)."""
-        from . import ops
-        shard, dev, world, rank = self.shard, self.shard.device, self.world, self.rank
-        n_queries = q.shape[0]
-        # (an empty shard goes through the same calls: every candidate is (-inf, -1))
-        # peer memory + global stage order: the pruning thresholds are shared across the GPUs as well
-        # (a shard's K'-th best bounds the global K'-th best only if the shard lists are as long as the global candidate
-        #  list: not the case for corpora so small that a shard holds fewer rows than that list)
-        kc = min(world * kp_glob, ops.overfetch_for(k_glob, self.n_total))
-        share_thr = peer is not None and two_phase and self.share_thresholds and kp_glob >= kc
-        if peer is not None:
-            ptrs, local = peer.slot(parity)                        # local: [world, cap, 2]
-        # ... and when this shard can fill the common list width, the strip merge stores the raw candidate list straight
-        # into every rank's gather buffer (no scatter kernel)
-        fused_scatter = share_thr and shard.n >= kp_glob
-        qd, q_inv, raw_s, cand = ops.topk_candidates(q, shard, k, overfetch=kp_glob,
-                                                     shared_thr=peer.thr_slot(parity) if share_thr else None,
-                                                     pair_dst=(ptrs, rank * peer.cap) if fused_scatter else None)
+    # ------------------------------------------------------------------------------------------ peer-memory pipelined step
+    def _sub_sizes(self, n_queries: int) -> List[int]:
+        """Sub-batches of one call: whole 256-query tiles; auto = 2 for >= 2048 queries, 4 for >= 32768."""
+        want = self.sub_batches if self.sub_batches > 0 else (4 if n_queries >= 32768 else 2 if n_queries >= 2048 else 1)
+        tiles = -(-n_queries // 256)
+        want = max(1, min(want, tiles))
+        per = -(-tiles // want) * 256
+        sizes = []
+        left = n_queries
+        while left > 0:
+            sizes.append(min(per, left))
+            left -= sizes[-1]
+        return sizes
 
-        def exchange(fill, width, region_off):
-            """fill(dst_ptrs, pair_offset) stores this rank's [Q, width] list; returns the gathered [world] lists as
-            (tensor, layout) ready for merge_pairs."""
-            if peer is not None:
-                fill(ptrs, rank * peer.cap + region_off)
-                peer.barrier()                                     # every peer's stores have landed
-                region = local[:, region_off:, :]                  # parts are peer.cap pairs apart
-                if region_off == 0:
-                    return ("strided", local)
-                return ("strided_off", region)
-            send = torch.empty((n_queries, width, 2), dtype=torch.int32, device=dev)
-            fill([send.data_ptr()], 0)
-            gathered = torch.empty((world, n_queries, width, 2), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gathered.view(world * n_queries, width, 2), send, group=self.group)
-            return ("dense", gathered)
-
-        def merged(kind_t, width, k_out):
-            kind, t = kind_t
-            # every list in flight was produced sorted by this library (strip merge / re-score): no per-list sort
-            if kind == "dense":
-                return ops.merge_pairs(t, k_out, parts_sorted=True)
-            if kind == "strided":
-                return ops.merge_pairs(t, k_out, n_queries=n_queries, k_in=width, parts_sorted=True)
-            return ops.merge_pairs_at(t, peer.cap, k_out, n_queries, width, parts_sorted=True)
-
-        if two_phase:
-            kp = cand.shape[1]
-            if kp < kp_glob:                                       # a small shard: pad its raw list to the common width
-                raw_s = torch.cat([raw_s, raw_s.new_full((n_queries, kp_glob - kp), float("-inf"))], dim=1).contiguous()
-                cand = torch.cat([cand, cand.new_full((n_queries, kp_glob - kp), -1)], dim=1).contiguous()
-            g1 = exchange((lambda d, off: None) if fused_scatter else (lambda d, off: ops.scatter_pairs(raw_s, cand, d, off)),
-                          kp_glob, 0)
-            if share_thr:
-                # between the step's two barriers: every rank is past this step's contraction, nobody can have begun the
-                # next one -- the other parity's thresholds (used by the next step) are cleared here
-                peer.thr[1 - parity, :n_queries].zero_()
-            _, cand_glob = merged(g1, kp_glob, kc)                 # the global K' candidates, identical on every rank
-            g2 = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand_glob, k_glob, d, dst_offset_pairs=off),
-                          k_glob, n_queries * kp_glob)
-            s, i = merged(g2, k_glob, k_glob)
-        else:
-            g = exchange(lambda d, off: ops.rescore_pairs(qd, q_inv, shard, cand, k_glob, d, dst_offset_pairs=off), k_glob, 0)
-            s, i = merged(g, k_glob, k_glob)
-        if peer is not None and advance:
-            peer.next_step()
-        return s, i.to(torch.int64)
-
-    def capture(self, queries, k: int) -> "GraphedSearch":
-        """Record the whole search step for `queries`' shape in CUDA graphs (one per exchange-buffer parity) and
-        return a callable that replays them: `s, i = graphed(new_queries)`; results live in static output buffers
-        until the next replay of the same parity."""
-        return GraphedSearch(self, queries, k)
-
-    def _peer_for(self, n_pairs: int, n_queries: int, dev: torch.device) -> Optional[_PeerExchange]:
-        """Symmetric gather buffers big enough for n_pairs per rank, or None (-> NCCL).  Collective: every rank
-        calls it with the same n_pairs and all of them agree on the outcome."""
-        if self._exchange_req == "nccl" or self._peer_failed:
-            return None
-        if self._peer is not None and self._peer.cap >= n_pairs and self._peer.q_cap >= n_queries:
-            return self._peer
-        ok = 1
-        peer = None
+    def _ring_for(self, n_queries: int, k: int) -> bool:
+        """Make sure the symmetric ring fits this call (COLLECTIVE: every rank calls it with the same arguments and all
+        agree on the outcome).  False -> fall back to the NCCL gather."""
+        if self._peer_failed:
+            return False
+        from . import _lib, ops
+        shard = self.shard
+        k_glob, kp, kc = self._widths(k)
+        q_sub = max(self._sub_sizes(n_queries)) if n_queries else 1
+        row_bytes = shard.rows.shape[1]
+        n_seg = len(shard.dims) if self._is_joint else 1
+        key = (kp, kc, row_bytes, n_seg)
+        old = self._rings.get(key)
+        if old is not None and old.fits(q_sub, kp, kc, row_bytes, n_seg):
+            self._ring = old
+            return True
+        dev = shard.device
+        ok, ring = 1, None
         try:
-            peer = _PeerExchange(self.group, self.world, n_pairs, n_queries, dev)
+            if old is not None:
+                torch.cuda.synchronize(dev)                       # nothing of the old ring is in flight
+                q_sub = max(q_sub, old.q_cap)
+            ring = _PeerRing(self.group, self.world, self.rank, q_sub, kp, kc, row_bytes, n_seg, dev)
         except Exception as e:  # noqa: BLE001
             ok = 0
             self._peer_error = repr(e)
@@ -300,16 +422,148 @@ class ShardedCorpus:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) != 1:
             self._peer_failed = True
-            self._peer = None
+            self._ring = None
             if self._exchange_req == "peer":
                 raise RuntimeError(f"exchange='peer' requested but symmetric memory is unavailable: {getattr(self, '_peer_error', 'a peer failed')}")
-            return None
-        self._peer = peer
+            return False
+        self._rings[key] = ring
+        self._ring = ring
         self.exchange = "peer"
-        return peer
+        return True
+
+    def _segment_tables(self, mats: List[torch.Tensor], row0: int, q_invs):
+        """ctypes tables of the re-score for the query rows starting at row0."""
+        from . import ops
+        shard = self.shard
+        cos = shard.metric == "cos"
+        if self._is_joint:
+            srcs, c_invs, dims, weights = shard.sources, shard.inv_norms, shard.dims, shard.weights
+        else:
+            srcs, c_invs, dims, weights = [shard.source], [shard.inv_norm], [shard.dim], [1.0]
+        return ops.segment_tables(mats, row0, [t if cos else None for t in q_invs], srcs, [t if cos else None for t in c_invs],
+                                  dims, weights)
+
+    def _prepare_queries(self, sub: List[torch.Tensor], ring: _PeerRing, slot: int):
+        """K1 on a sub-batch into the slot's scratch -> (prepared rows, [inv_norm per modality])."""
+        from . import _lib, joint, ops
+        shard = self.shard
+        n = sub[0].shape[0]
+        if self._is_joint:
+            rows, invs = joint._cast_segments(sub, shard.op, _lib.SIDE_QUERY, shard.metric == "cos", shard.eps, shard.weights,
+                                              shard.seg_bytes, sum(shard.seg_bytes), out=(ring.q_rows[slot], ring.q_inv[slot]))
+            return rows, invs
+        rows, inv = ops.normalize_cast(sub[0], shard.op, _lib.SIDE_QUERY, shard.metric == "cos", shard.eps,
+                                       out=(ring.q_rows[slot], ring.q_inv[slot][0]))
+        return rows, [inv]
+
+    def _run_pipelined(self, mats: List[torch.Tensor], k: int, ev_in):
+        """Enqueue one query batch (device matrices, ready on the current stream and -- if given -- at `ev_in`) as pipelined
+        sub-steps.  Returns (scores, rows, event that fires when the results are complete).  Nothing here blocks the host."""
+        from . import _lib, ops
+        lib = _lib.load()
+        shard, dev, world, rank, ring = self.shard, self.shard.device, self.world, self.rank, self._ring
+        c_stream, t_stream, _, _ = self._pipe_streams()
+        n_queries = mats[0].shape[0]
+        k_glob, kp, kc = self._widths(k)
+        out_s = torch.empty((n_queries, k_glob), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n_queries, k_glob), dtype=torch.int64, device=dev)
+        if n_queries == 0:
+            return out_s, out_i, None
+        capturing = torch.cuda.is_current_stream_capturing()
+        op = ops._OP_DTYPE[shard.op]
+        # a shard's K'-th best bounds the global K'-th best only if every shard's list is as long as the global candidate list
+        share_thr = self.share_thresholds and kp >= kc and self._min_local >= kc
+        k_loc = max(1, min(kp, shard.n))
+        part_stride = ring.q_cap * kp
+        sizes = self._sub_sizes(n_queries)
+        if shard.n > 0:
+            ring.ensure_workspace(max(int(lib.mmd_topk_workspace_bytes(n, shard.n, shard.dim, op, k_loc)) for n in set(sizes)))
+        else:
+            ring.ensure_workspace(8)
+        # the internal streams start behind the caller's stream as of NOW: the queries are ready there, and the freshly
+        # allocated outputs (caller's pool) may reuse memory whose last use was enqueued there
+        ev_now = torch.cuda.Event()
+        ev_now.record(torch.cuda.current_stream(dev))
+        c_stream.wait_event(ev_now)
+        if ev_in is not None:
+            c_stream.wait_event(ev_in)
+        row0 = 0
+        # under CUDA-graph capture the events must belong to the capture; replays of a graph are serialised as a whole, so
+        # the cross-step wait is only needed (and only legal) between sub-steps of the same capture
+        ev_c = [torch.cuda.Event() for _ in sizes] if capturing else None
+        ev_f = [torch.cuda.Event() for _ in sizes] if capturing else None
+        for j, n in enumerate(sizes):
+            step = ring.step
+            slot = step % RING
+            sub = [m[row0:row0 + n] for m in mats]
+            e_c = ev_c[j] if capturing else ring.ev_c[slot]
+            e_f = ev_f[j] if capturing else ring.ev_f[slot]
+            # ---- stage C
+            with torch.cuda.stream(c_stream):
+                if capturing:
+                    if j >= 2:
+                        c_stream.wait_event(ev_f[j - 2])
+                elif step >= 2:
+                    c_stream.wait_event(ring.ev_f[(step - 2) % RING])          # slot free on every rank (see module docstring)
+                q_rows, q_invs = self._prepare_queries(sub, ring, slot)
+                ops.sharded_candidates(q_rows, n, shard, k_loc, ring.raw_s[slot], ring.raw_i[slot], ring.ws[slot], ring.thr_all(slot),
+                                       rank, share_thr, ring.gather_all(slot), rank * part_stride, kp, ring.flags_arrive(0),
+                                       ring.sync_ptr(0))
+                e_c.record(c_stream)
+            # ---- stages X and F
+            with torch.cuda.stream(t_stream):
+                t_stream.wait_event(e_c)
+                ops.exchange_rescore(ring.gather_all(slot)[rank], world, part_stride, n, kp, kc, self._segment_tables(mats, row0, q_invs),
+                                     shard.n, shard.idx_offset, ring.resc_all(slot), rank, dev, ring.flags_local(0), world,
+                                     ring.flags_arrive(1), ring.sync_ptr(1))
+                ops.exchange_finish(ring.resc_all(slot)[rank], n, kc, k_glob, out_s.data_ptr() + row0 * k_glob * 4,
+                                    out_i.data_ptr() + row0 * k_glob * 8, True, dev, ring.flags_local(1), world, ring.sync_ptr(2))
+                e_f.record(t_stream)
+            ring.step += 1
+            row0 += n
+        done = torch.cuda.Event()
+        with torch.cuda.stream(t_stream):
+            done.record(t_stream)
+        return out_s, out_i, done
+
+    # ------------------------------------------------------------------------------------------ plain gather variants
+    def _topk_gather(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """NCCL variant on the current stream: local lists (re-scored per shard, or raw candidates first and the global
+        candidates re-scored after a first gather), `all_gather_into_tensor`, K4 merge."""
+        from . import joint, ops
+        shard, dev, world = self.shard, self.shard.device, self.world
+        if not self._has_source() or self._is_joint or self.rescore == "local":
+            return self._topk_generic(queries, k)
+        k_glob, kp, kc = self._widths(k)
+        q = self.upload_queries(queries)[0]
+        n_queries = q.shape[0]
+        qd, q_inv, raw_s, cand = ops.topk_candidates(q, shard, k, overfetch=kp)
+        if cand.shape[1] < kp:                                   # a small shard: pad its raw list to the common width
+            pad = kp - cand.shape[1]
+            raw_s = torch.cat([raw_s, raw_s.new_full((n_queries, pad), float("-inf"))], dim=1).contiguous()
+            cand = torch.cat([cand, cand.new_full((n_queries, pad), -1)], dim=1).contiguous()
+
+        def gather(fill, width):
+            send = torch.empty((n_queries, width, 2), dtype=torch.int32, device=dev)
+            fill(send)
+            gathered = torch.empty((world, n_queries, width, 2), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gathered.view(world * n_queries, width, 2), send, group=self.group)
+            return gathered
+
+        g1 = gather(lambda send: ops.scatter_pairs(raw_s, cand, [send.data_ptr()], 0), kp)
+        _, cand_glob = ops.merge_pairs(g1, kc, parts_sorted=True)
+        g2 = gather(lambda send: ops.rescore_pairs(qd, q_inv, shard, cand_glob, k_glob, [send.data_ptr()], 0), k_glob)
+        s, i = ops.merge_pairs(g2, k_glob, parts_sorted=True)
+        return s, i.to(torch.int64)
+
+    def capture(self, queries, k: int) -> "GraphedSearch":
+        """Record the whole search step for `queries`' shape in a CUDA graph and return a callable that replays it:
+        `s, i = graphed(new_queries)`; results live in static output buffers until the next replay."""
+        return GraphedSearch(self, queries, k)
 
     def _topk_generic(self, queries, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Same plumbing with separate score / row tensors and injectable stages (CPU tests; corpora without source)."""
+        """Same plumbing with separate score / row tensors and injectable stages (CPU tests; corpora without source;
+        re-score per shard)."""
         k_glob = min(k, self.n_total)
         s_loc, i_loc = self._local_topk(queries, self.shard, k)          # [Q, min(k, n_local)], global rows
         n_queries = s_loc.shape[0]
@@ -333,51 +587,48 @@ class ShardedCorpus:
         return s, i.to(torch.int64)
 
 
+def _cuda_local_topk_i64(queries, shard, k, phases=1):
+    from . import joint, ops
+    if isinstance(shard, joint.JointCorpus):
+        return joint.topk_joint(queries, shard, k)
+    return ops.topk(queries, shard, k, phases=phases)
+
+
 class GraphedSearch:
-    """A ShardedCorpus search step frozen into CUDA graphs (all kernels + the exchange), replayed per query batch."""
+    """A ShardedCorpus search step frozen into a CUDA graph (all kernels of all stages, both internal streams), replayed per
+    query batch.  The flag sequence numbers of the exchange live in device memory, so a replay is a valid next step."""
 
     def __init__(self, sc: ShardedCorpus, queries, k: int):
         from . import ops
-        if sc._injected or sc.shard.source is None:
+        if sc._injected or not sc._has_source():
             raise RuntimeError("capture() needs the CUDA path with source embeddings kept (exact re-score)")
+        if sc._is_joint:
+            raise RuntimeError("capture() supports single-modality corpora")
         self.sc, self.k = sc, k
         dev = sc.shard.device
         q = ops._as_rows(queries, dev)
         self.q_static = q.clone()
-        n_queries = q.shape[0]
-        k_glob = min(k, sc.n_total)
-        kp_glob = ops.overfetch_for(min(k, sc._max_local), sc._max_local)
-        two_phase = sc.rescore == "global" and sc.world > 1
-        self.peer = None
-        if sc.world > 1:
-            cap = n_queries * (kp_glob + k_glob) if two_phase else n_queries * k_glob
-            sc.topk(self.q_static, k)                              # warm-up: lazy initialisation (attributes, symmetric memory)
-            if sc.exchange == "peer":
-                self.peer = _PeerExchange(sc.group, sc.world, cap, n_queries, dev)      # this object's own double buffer
-        else:
-            ops.topk(self.q_static, sc.shard, k)
+        self.peer = sc.world > 1
+        sc.topk(self.q_static, k)                                  # warm-up: lazy initialisation (attributes, symmetric memory)
+        if self.peer and sc.exchange != "peer":
+            raise RuntimeError("capture() with several ranks needs exchange='peer' (NCCL collectives are not captured here)")
         torch.cuda.synchronize(dev)
-        self.graphs, self.outs = [], []
-        self.launches_per_step = 0
-        n_graphs = 2 if self.peer is not None else 1
+        if self.peer:
+            dist.barrier(group=sc.group)
         stream = torch.cuda.Stream(device=dev)
-        for parity in range(n_graphs):
-            g = torch.cuda.CUDAGraph()
-            n0 = ops.launch_count()
-            with torch.cuda.graph(g, stream=stream):
-                if sc.world > 1:
-                    out = sc._search(self.q_static, k, k_glob, kp_glob, self.peer, two_phase, parity, advance=False)
-                else:
-                    out = ops.topk(self.q_static, sc.shard, k)
-            self.launches_per_step = ops.launch_count() - n0      # this library's kernels inside one replay
-            self.graphs.append(g)
-            self.outs.append(out)
+        self.graphs, self.outs = [], []
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g, stream=stream):
+            out = sc.topk(self.q_static, k)
+        self.launches_per_step = ops.launch_count() - n0          # this library's kernels inside one replay
+        self.graphs.append(g)
+        self.outs.append(out)
         self.calls = 0
 
     def __call__(self, queries=None):
         if queries is not None:
             self.sc.upload_queries(queries, out=self.q_static)
-        j = self.calls % len(self.graphs)
         self.calls += 1
-        self.graphs[j].replay()
-        return self.outs[j]
+        self.graphs[0].replay()
+        return self.outs[0]

@@ -119,3 +119,12 @@ def compare_topk(dev_scores: torch.Tensor, dev_idx: torch.Tensor, oracle_full: t
     rel = err / picked.abs().clamp_min(1e-30)
     return TopkComparison(n_q, same_set, same_order, excused, bad, float(err.max()) if err.numel() else 0.0,
                           float(rel.max()) if rel.numel() else 0.0)
+
+
+def recall_at_k(dev_idx: torch.Tensor, oracle_full: torch.Tensor, k: int) -> float:
+    """Fraction of the oracle's top-k rows (by (score desc, row asc)) that the device lists contain -- the bar for the lossy
+    fp8 candidate pass, for which BASELINE.json states no tolerance."""
+    _, o_idx = ordered_topk(oracle_full, k)
+    d = dev_idx.cpu().long()[:, :k].tolist()
+    hit = sum(len(set(a) & set(b)) for a, b in zip(d, o_idx.tolist()))
+    return hit / float(o_idx.numel())

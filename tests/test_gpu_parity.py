@@ -406,6 +406,79 @@ def test_global_rescore_flow_with_shared_thresholds_emulated_on_one_gpu(m):
     assert i[0, :2].tolist() == [7, 20010]
 
 
+@pytest.mark.parametrize("k,n_rows,joint", [(10, 20011, False), (100, 9001, False), (10, 41, False), (10, 7001, True)])
+def test_three_stage_exchange_emulated_on_one_gpu(m, k, n_rows, joint):
+    """The sharded step of mmd_retrieval.sharded, stage by stage (C: mmd_sharded_candidates, X: mmd_exchange_rescore,
+    F: mmd_exchange_finish), with three 'ranks' run one after the other on one device and NO flags (n_wait = n_arrive = 0:
+    kernels that wait for one another must not share a GPU).  Every rank's gather / re-score buffer is its own allocation,
+    written by all ranks -- as with peer-mapped buffers.  Must equal the unsharded result bit for bit."""
+    from mmd_retrieval import ops, joint as jt, _lib
+    from mmd_retrieval.sharded import shard_bounds
+    world, n_q = 3, 300
+    if joint:
+        dims, weights = (256, 128), (0.6, 0.4)
+        cs = [_data("text", n_rows, d, 70 + j) for j, d in enumerate(dims)]
+        qs = [_data("text", n_q, d, 80 + j) for j, d in enumerate(dims)]
+        want_s, want_i = m.topk_joint([x.cuda() for x in qs], m.prepare_joint([x.cuda() for x in cs], weights), k)
+    else:
+        cs, qs = [_data("text", n_rows, 768, 66)], [_data("text", n_q, 768, 67)]
+        cs[0][n_rows - 1] = cs[0][7]                                  # equal scores on different shards
+        qs[0][0] = cs[0][7] * 1.5
+        want_s, want_i = m.topk(qs[0].cuda(), cs[0].cuda(), k)
+    q_dev = [x.cuda() for x in qs]
+    max_local = -(-n_rows // world)
+    k_glob = min(k, n_rows)
+    kp = ops.overfetch_for(min(k, max_local), max_local)
+    kc = min(world * kp, ops.overfetch_for(k_glob, n_rows))
+    share = kp >= kc and n_rows // world >= kc
+    part_stride = n_q * kp
+    gather = [torch.full((world * part_stride, 2), 7, dtype=torch.int32, device="cuda") for _ in range(world)]
+    resc = [torch.full((n_q * kc, 2), 7, dtype=torch.int32, device="cuda") for _ in range(world)]
+    thr = [torch.zeros((n_q,), dtype=torch.int32, device="cuda") for _ in range(world)]
+    shards, q_invs = [], None
+    for r in range(world):                                          # stage C on every rank
+        lo, hi = shard_bounds(n_rows, world, r)
+        if joint:
+            pc = m.prepare_joint([x[lo:hi].cuda() for x in cs], weights, idx_offset=lo)
+            q_rows, q_invs = jt._cast_segments(q_dev, pc.op, _lib.SIDE_QUERY, True, pc.eps, pc.weights, pc.seg_bytes, sum(pc.seg_bytes))
+        else:
+            pc = m.prepare_corpus(cs[0][lo:hi].cuda(), idx_offset=lo)
+            q_rows, inv = ops.normalize_cast(q_dev[0], pc.op, _lib.SIDE_QUERY, True, pc.eps)
+            q_invs = [inv]
+        shards.append(pc)
+        k_loc = max(1, min(kp, pc.n))
+        raw_s = torch.empty((n_q, kp), dtype=torch.float32, device="cuda")
+        raw_i = torch.empty((n_q, kp), dtype=torch.int32, device="cuda")
+        ws = torch.empty((max(8, int(_lib.load().mmd_topk_workspace_bytes(n_q, max(pc.n, 1), pc.dim, ops._OP_DTYPE[pc.op], k_loc))),),
+                         dtype=torch.uint8, device="cuda")
+        ops.sharded_candidates(q_rows, n_q, pc, k_loc, raw_s, raw_i, ws, [t.data_ptr() for t in thr], r, share,
+                               [g.data_ptr() for g in gather], r * part_stride, kp)
+    torch.cuda.synchronize()
+    for g in gather[1:]:
+        assert torch.equal(g, gather[0])
+    lists = gather[0].view(world, n_q, kp, 2)
+    assert bool((lists[..., 1] >= -1).all()) and bool((lists[..., 1] < n_rows).all())      # every slot written, padded with -1
+    for r in range(world):                                          # stage X: every rank re-scores what it owns
+        pc = shards[r]
+        if joint:
+            tables = ops.segment_tables(q_dev, 0, q_invs, pc.sources, pc.inv_norms, pc.dims, pc.weights)
+        else:
+            tables = ops.segment_tables(q_dev, 0, q_invs, [pc.source], [pc.inv_norm], [pc.dim], [1.0])
+        ops.exchange_rescore(gather[r].data_ptr(), world, part_stride, n_q, kp, kc, tables, pc.n, pc.idx_offset,
+                             [x.data_ptr() for x in resc], r, pc.device)
+    torch.cuda.synchronize()
+    for r in range(world):                                          # stage F on every rank: identical lists everywhere
+        out_s = torch.empty((n_q, k_glob), dtype=torch.float32, device="cuda")
+        out_i = torch.empty((n_q, k_glob), dtype=torch.int64, device="cuda")
+        ops.exchange_finish(resc[r].data_ptr(), n_q, kc, k_glob, out_s.data_ptr(), out_i.data_ptr(), True, out_s.device)
+        assert torch.equal(out_i, want_i) and torch.equal(out_s, want_s), r
+    out_i32 = torch.empty((n_q, k_glob), dtype=torch.int32, device="cuda")
+    ops.exchange_finish(resc[0].data_ptr(), n_q, kc, k_glob, out_s.data_ptr(), out_i32.data_ptr(), False, out_s.device)
+    assert torch.equal(out_i32.long(), want_i)
+    if not joint and n_rows > 100:
+        assert out_i[0, :2].tolist() == [7, n_rows - 1]
+
+
 # ------------------------------------------------------------------------------------------ joint image+text fusion
 @pytest.mark.parametrize("op,dims,weights", [("bf16", (512, 512), (0.5, 0.5)), ("bf16", (768, 2048), (0.7, 0.3)),
                                              ("fp16", (100, 36), (0.25, 0.75)), ("bf16", (64, 64, 32), (0.2, 0.3, 0.5))])
