@@ -203,7 +203,12 @@ MMD_API int mmd_sharded_candidates(const void* q_prep, const void* c_prep, int o
                            int64_t idx_offset, float* out_scores, int32_t* out_idx, void* workspace,
                            size_t workspace_bytes, uint32_t* thr_local, void* const* thr_all_host, int n_thr, int reset_thr,
                            void* const* pair_dst_host, int n_pair_dst, int64_t pair_offset, int pair_width,
-                           void* const* arrive_flags_host, int n_arrive, uint32_t* sync_state, void* stream);
+                           void* const* arrive_flags_host, int n_arrive, uint32_t* sync_state, void* stream,
+                           void* merge_stream);
+/* (merge_stream: NULL, or a second stream on which the strip merge -- and with it the stores to the peers and the flag --
+ * runs behind an event recorded after the contraction, so that the next contraction on `stream` need not wait for it.)
+ * Zero n 32-bit words on `stream` (the shared threshold array of a step, reset before anyone publishes into it). */
+MMD_API int mmd_zero_u32(uint32_t* dst, int64_t n, void* stream);
 
 /* Stage X: wait; merge the `parts` sorted candidate lists of every query (gathered: part p starts p * part_stride_pairs
  * pairs in, [Q][k_in] pairs each) into the global candidate list of kc entries (identical on every rank); re-score in

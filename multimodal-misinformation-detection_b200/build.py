@@ -26,8 +26,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 INCLUDE = HERE.parent / "include"
 OUT_DIR = HERE / "mmd_retrieval"
-LIB = OUT_DIR / "libmmd.so"
-INFO = OUT_DIR / "libmmd.so.buildinfo"
+LIB = Path(os.environ["MMD_BUILD_OUT"]).resolve() if os.environ.get("MMD_BUILD_OUT") else OUT_DIR / "libmmd.so"   # developer builds
+INFO = LIB.with_name(LIB.name + ".buildinfo")
 OBJ_DIR = HERE / "build"
 
 SOURCES = ["api.cu", "normalize.cu", "topk_fused.cu", "topk_merge.cu", "rescore.cu", "dedupe.cu", "exchange.cu"]
@@ -52,7 +52,10 @@ def _nvcc_version(nvcc: str) -> str:
 
 
 def _extra_flags() -> list:
-    return ["-DMMD_STATS"] if os.environ.get("MMD_STATS") else []      # developer build: per-tile timeline in the fused kernel
+    """Developer builds: MMD_STATS=1 (per-tile timeline in the fused kernel), MMD_DEFINES="A=1,B=2" (extra -D switches)."""
+    flags = ["-DMMD_STATS"] if os.environ.get("MMD_STATS") else []
+    flags += [f"-D{d}" for d in os.environ.get("MMD_DEFINES", "").split(",") if d]
+    return flags
 
 
 def source_hash(nvcc_version: str) -> str:

@@ -59,7 +59,8 @@ SIGNATURES = {
     "mmd_sharded_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
                                          C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.c_int,
-                                         C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_zero_u32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "mmd_exchange_rescore": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                        C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),

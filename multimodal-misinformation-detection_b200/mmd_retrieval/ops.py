@@ -447,19 +447,28 @@ def _vp(ptrs: Sequence[int]):
 
 def sharded_candidates(q_rows: torch.Tensor, n_queries: int, corpus, k_loc: int, raw_s: torch.Tensor, raw_i: torch.Tensor,
                        ws: torch.Tensor, thr_all: Sequence[int], own: int, share_thr: bool, gather_ptrs: Sequence[int],
-                       pair_offset: int, pair_width: int, arrive_ptrs: Sequence[int] = (), sync_ptr: int = 0) -> None:
+                       pair_offset: int, pair_width: int, arrive_ptrs: Sequence[int] = (), sync_ptr: int = 0,
+                       reset_thr: bool = True, merge_stream=None) -> None:
     """Stage C of a sharded step (mmd_sharded_candidates) on the current stream: fused top-k_loc over this rank's shard; the
-    strip merge stores the list, padded to pair_width, at pair pair_offset + q * pair_width into every gather buffer and
-    raises the arrive flags.  corpus: PreparedCorpus or JointCorpus (rows / op / n / dim / idx_offset are used)."""
+    strip merge (on merge_stream, if given) stores the list, padded to pair_width, at pair pair_offset + q * pair_width into
+    every gather buffer and raises the arrive flags.  corpus: PreparedCorpus or JointCorpus (rows / op / n / dim / idx_offset
+    are used)."""
     dev = corpus.device
     with torch.cuda.device(dev):
         rc = _lib.load().mmd_sharded_candidates(
             _ptr(q_rows), C.c_void_p(corpus.rows.data_ptr() if corpus.n else 0), _OP_DTYPE[corpus.op], n_queries, corpus.n, corpus.dim,
             k_loc, corpus.idx_offset, _ptr(raw_s), _ptr(raw_i), _ptr(ws), ws.numel(),
-            C.c_void_p(int(thr_all[own]) if thr_all else 0), _vp(thr_all), len(thr_all) if share_thr else 0, 1,
+            C.c_void_p(int(thr_all[own]) if thr_all else 0), _vp(thr_all), len(thr_all) if share_thr else 0, int(reset_thr),
             _vp(gather_ptrs), len(gather_ptrs), int(pair_offset), int(pair_width),
-            _vp(arrive_ptrs), len(arrive_ptrs), C.c_void_p(int(sync_ptr)), _stream_ptr(dev))
+            _vp(arrive_ptrs), len(arrive_ptrs), C.c_void_p(int(sync_ptr)), _stream_ptr(dev),
+            C.c_void_p(0 if merge_stream is None else merge_stream.cuda_stream))
     _lib.check(rc, "mmd_sharded_candidates")
+
+
+def zero_u32(ptr: int, n: int, device: torch.device) -> None:
+    """n 32-bit words at device pointer `ptr` <- 0 on the current stream (memset node, no kernel)."""
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().mmd_zero_u32(C.c_void_p(int(ptr)), int(n), _stream_ptr(device)), "mmd_zero_u32")
 
 
 def segment_tables(q_mats: Sequence[torch.Tensor], row0: int, q_invs: Sequence[Optional[torch.Tensor]], c_srcs: Sequence[torch.Tensor],

@@ -239,7 +239,7 @@ class ShardedCorpus:
     def _pipe_streams(self):
         if self._streams is None:
             dev = self.shard.device
-            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))     # contraction, tail, h2d, d2h
+            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(5))     # contraction, tail, h2d, d2h, query K1
         return self._streams
 
     def _widths(self, k: int) -> Tuple[int, int, int]:
@@ -282,7 +282,7 @@ class ShardedCorpus:
                 yield self._topk_generic(b, k)
             return
         dev = self.shard.device
-        c_stream, t_stream, h2d, d2h = self._pipe_streams()
+        c_stream, t_stream, h2d, d2h, _ = self._pipe_streams()
         cur = torch.cuda.current_stream(dev)
         pending = deque()
         plain = self.world > 1 and (not self._has_source() or self.rescore == "local" or self._exchange_req == "nccl")
@@ -380,8 +380,10 @@ class ShardedCorpus:
 
     # ------------------------------------------------------------------------------------------ peer-memory pipelined step
     def _sub_sizes(self, n_queries: int) -> List[int]:
-        """Sub-batches of one call: whole 256-query tiles; auto = 2 for >= 2048 queries, 4 for >= 32768."""
-        want = self.sub_batches if self.sub_batches > 0 else (4 if n_queries >= 32768 else 2 if n_queries >= 2048 else 1)
+        """Sub-batches of one call (whole 256-query tiles).  Default 1: every contraction launch pays its own cold start and
+        tail quantisation (measured at 2 GPUs, C3: two half-batch launches cost 0.18 ms more kernel time than one), which is
+        what a split would hide of the exchange tail; successive batches overlap through topk_stream() instead."""
+        want = self.sub_batches if self.sub_batches > 0 else 1
         tiles = -(-n_queries // 256)
         want = max(1, min(want, tiles))
         per = -(-tiles // want) * 256
@@ -462,7 +464,7 @@ class ShardedCorpus:
         from . import _lib, ops
         lib = _lib.load()
         shard, dev, world, rank, ring = self.shard, self.shard.device, self.world, self.rank, self._ring
-        c_stream, t_stream, _, _ = self._pipe_streams()
+        c_stream, t_stream, _, _, k_stream = self._pipe_streams()
         n_queries = mats[0].shape[0]
         k_glob, kp, kc = self._widths(k)
         out_s = torch.empty((n_queries, k_glob), dtype=torch.float32, device=dev)
@@ -484,35 +486,46 @@ class ShardedCorpus:
         # allocated outputs (caller's pool) may reuse memory whose last use was enqueued there
         ev_now = torch.cuda.Event()
         ev_now.record(torch.cuda.current_stream(dev))
-        c_stream.wait_event(ev_now)
+        k_stream.wait_event(ev_now)
         if ev_in is not None:
-            c_stream.wait_event(ev_in)
+            k_stream.wait_event(ev_in)
         row0 = 0
         # under CUDA-graph capture the events must belong to the capture; replays of a graph are serialised as a whole, so
-        # the cross-step wait is only needed (and only legal) between sub-steps of the same capture
-        ev_c = [torch.cuda.Event() for _ in sizes] if capturing else None
+        # the cross-step waits are only needed (and only legal) between sub-steps of the same capture
+        ev_k = [torch.cuda.Event() for _ in sizes] if capturing else None
         ev_f = [torch.cuda.Event() for _ in sizes] if capturing else None
         for j, n in enumerate(sizes):
             step = ring.step
             slot = step % RING
             sub = [m[row0:row0 + n] for m in mats]
-            e_c = ev_c[j] if capturing else ring.ev_c[slot]
+            e_k = ev_k[j] if capturing else ring.ev_c[slot]
             e_f = ev_f[j] if capturing else ring.ev_f[slot]
-            # ---- stage C
+            # ---- query side of stage C on its own stream (hides under the previous contraction): reset of the slot's shared
+            # thresholds + K1.  The slot was last used by step - 3: its stage F must be over (then this rank has seen flag
+            # set 1 of that step, i.e. no peer can still publish a bound of those queries; and the scratch is free).
+            with torch.cuda.stream(k_stream):
+                if capturing:
+                    if j >= RING:
+                        k_stream.wait_event(ev_f[j - RING])
+                elif step >= RING:
+                    k_stream.wait_event(ring.ev_f[slot])
+                if share_thr:
+                    ops.zero_u32(ring.thr_all(slot)[rank], n, dev)
+                q_rows, q_invs = self._prepare_queries(sub, ring, slot)
+                e_k.record(k_stream)
+            # ---- stage C: the contraction; its strip merge (+ stores to the peers + flag set 1) goes to the tail stream
             with torch.cuda.stream(c_stream):
+                c_stream.wait_event(e_k)
                 if capturing:
                     if j >= 2:
                         c_stream.wait_event(ev_f[j - 2])
                 elif step >= 2:
                     c_stream.wait_event(ring.ev_f[(step - 2) % RING])          # slot free on every rank (see module docstring)
-                q_rows, q_invs = self._prepare_queries(sub, ring, slot)
                 ops.sharded_candidates(q_rows, n, shard, k_loc, ring.raw_s[slot], ring.raw_i[slot], ring.ws[slot], ring.thr_all(slot),
                                        rank, share_thr, ring.gather_all(slot), rank * part_stride, kp, ring.flags_arrive(0),
-                                       ring.sync_ptr(0))
-                e_c.record(c_stream)
+                                       ring.sync_ptr(0), reset_thr=False, merge_stream=t_stream)
             # ---- stages X and F
             with torch.cuda.stream(t_stream):
-                t_stream.wait_event(e_c)
                 ops.exchange_rescore(ring.gather_all(slot)[rank], world, part_stride, n, kp, kc, self._segment_tables(mats, row0, q_invs),
                                      shard.n, shard.idx_offset, ring.resc_all(slot), rank, dev, ring.flags_local(0), world,
                                      ring.flags_arrive(1), ring.sync_ptr(1))

@@ -128,7 +128,8 @@ def _worker_small(rank, world, port, out):
                 want = min(10, n_rows)
                 assert tuple(iv.shape) == (64 + it, want), (n_rows, iv.shape)
                 cmp = exact.compare_topk(sv, iv, exact.exact_scores(qq, corpus[:n_rows]), want, tie_tol=2e-6)
-                assert cmp.ok and cmp.max_rel_score_err <= 1e-5, (n_rows, it, cmp)
+                # (256-d random pairs score ~0.06 and sometimes ~0.001: fp32 rounding is then > 1e-5 RELATIVE; bound it absolutely)
+                assert cmp.ok and (cmp.max_rel_score_err <= 1e-5 or cmp.max_score_err <= 2e-7), (n_rows, it, cmp)
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
