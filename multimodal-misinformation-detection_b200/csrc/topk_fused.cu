@@ -22,6 +22,7 @@
 // Every unit leaves a sorted K-list per query; topk_merge.cu folds the strips together.
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <utility>
@@ -68,6 +69,9 @@ struct FusedParams {
   int stages;
   int a_rows;            // query rows staged per CTA and K block: 128, or the 32-row groups a batch of < 128 queries fills
   int key_warps;         // epilogue warps (lane quarters 0 .. key_warps-1) that own candidate buffers: a_rows / 32
+  int trig_level;        // a row holding more than this many candidates triggers a compaction of the warp's rows
+  int target_hi;         // a compaction leaves between kprime and this many candidates in a row
+  int joint_after;       // compactions within one tile after which the next tile is bounded jointly up front (0 = never)
   uint64_t* partial;     // [Q][S][kprime] keys
   uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
   uint32_t* thr_peer[8]; // row-sharded corpus: the same array on EVERY rank (peer-mapped, own one included); a bound
@@ -129,11 +133,10 @@ __device__ __forceinline__ uint64_t raw_to_key(uint32_t score_bits, uint32_t col
   return (static_cast<uint64_t>(float_to_ordered(__uint_as_float(score_bits))) << 32) | colword;
 }
 
-// Largest entry count a compaction may leave behind: K' plus some slack (a wider window converges in fewer passes), but
-// always at least 16 free slots (8 for the group of appends that triggered the compaction).
-__host__ __device__ constexpr int compaction_target(int cap, int kprime) {
-  const int slack = (cap - kprime) / 3 > 8 ? (cap - kprime) / 3 : 8;
-  const int want = kprime + slack;
+// Largest entry count a compaction may leave behind: K' plus a small window (a wider window converges in fewer passes but
+// leaves a looser bound, and the bound is what keeps the collect pass rare), always at least 16 free slots.
+__host__ __device__ constexpr int compaction_target(int cap, int kprime, int window) {
+  const int want = kprime + window;
   const int most = cap - 16;
   return want < most ? want : (most > kprime ? most : kprime);
 }
@@ -361,17 +364,31 @@ __device__ __forceinline__ float chunk_max(const uint32_t* r) {
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 
-// Cold start of a row with a long list (K' > 32): tau such that between K' and target_hi of the tile's (valid) scores lie
-// above it, found by bisection on the score value; every pass re-reads the 256-column accumulator tile from TMEM
-// (double-buffered 32-column loads) and counts.  Returns -inf for rows that do not `want` a bound, whose tile holds fewer
-// than K' valid scores, or whose bisection cannot converge (then the row simply collects everything, as before).
-__device__ __noinline__ float tile_bound_by_bisection(uint32_t tile_addr, bool edge, int64_t col_tile, int64_t N, int kprime,
-                                                      int target_hi, bool want) {
+// Joint bound of (a row's candidate buffer + the accumulator tile that is about to be collected), found BEFORE the tile is
+// collected: tau such that between K' and target_hi of {buffer entries, tile scores} lie above it.  The buffer is then
+// partitioned by tau in place and tau becomes the row's bound, so the collect pass that follows appends at most
+// target_hi - (entries kept) scores and never overflows.  Used where scores arrive faster than a compaction frees slots:
+// the first tiles of a cold row (thr = -inf; for K' > 32 this replaces the group-maxima trick) and any tile that follows
+// one with several compactions.  Bisection on the score value; a pass counts buffer entries (shared memory) and tile
+// scores (TMEM, double-buffered 32-column loads) above the midpoint -- thread <-> row, no shuffles.  Rows that do not need
+// it (fewer than target_hi + 1 scores above their bound), rows without K' scores yet, and rows whose bisection cannot
+// converge (equal scores straddling the K'-th best) are left alone; the regular collect + compaction handles them.
+// Returns true (warp-uniform) if any row needed tightening.
+__device__ __noinline__ bool joint_bound(uint32_t tile_addr, int ncols, uint32_t s_addr, uint32_t c_addr, int kprime, int target_hi,
+                                         bool valid, int& cnt, float& thr) {
   const float kNegInf = __uint_as_float(kNegInfBits);
   const float kPosInf = __uint_as_float(0x7f800000u);
-  const int ncols = edge ? static_cast<int>(N - col_tile) : kTileN;        // valid columns of this tile (warp-uniform)
+  const int maxcnt = __reduce_max_sync(kFullMask, valid ? cnt : 0);
   float mn = kPosInf, mx = kNegInf;
-  int nvalid = 0;
+#pragma unroll 4
+  for (int i = 0; i < maxcnt; ++i) {
+    const float v = __uint_as_float(ld_shared_b32(s_addr + i * kSlotStride));
+    const bool own = i < cnt;
+    st_shared_b32_pred(s_addr + i * kSlotStride, kNegInfBits, !own);
+    mn = fminf(mn, own ? v : kPosInf);
+    mx = fmaxf(mx, own ? v : kNegInf);
+  }
+  int nvalid = 0, above = 0;
   {
     uint32_t ra[32], rb[32];
     tmem_ld_32x32b_x32(tile_addr, ra);
@@ -386,6 +403,7 @@ __device__ __noinline__ float tile_bound_by_bisection(uint32_t tile_addr, bool e
         mn = fminf(mn, ok ? x : kPosInf);
         mx = fmaxf(mx, ok ? x : kNegInf);
         nvalid += ok ? 1 : 0;
+        above += (ok && x > thr) ? 1 : 0;
       }
       tmem_ld_wait();
       if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(tile_addr + (c + 2) * 32, ra);
@@ -396,18 +414,23 @@ __device__ __noinline__ float tile_bound_by_bisection(uint32_t tile_addr, bool e
         mn = fminf(mn, ok ? x : kPosInf);
         mx = fmaxf(mx, ok ? x : kNegInf);
         nvalid += ok ? 1 : 0;
+        above += (ok && x > thr) ? 1 : 0;
       }
     }
   }
-  want = want && nvalid >= kprime;
-  // invariant: count(> lo) = c_lo >= K'  and  count(> hi) < K'
-  float lo = pred_float(mn), hi = mx;
-  int c_lo = nvalid;
-  bool done = !want || c_lo <= target_hi;
-  bool ok = done;
-  for (int it = 0; it < 28 && __any_sync(kFullMask, !done); ++it) {
+  // invariant: count(> lo) = c_lo >= K'  and  count(> hi) < K'   (counts over buffer + tile)
+  const bool cold = !(thr > kNegInf);
+  float lo = cold ? pred_float(mn) : thr;
+  int c_lo = cold ? cnt + nvalid : cnt + above;
+  float hi = mx;
+  const bool want = valid && c_lo > target_hi;
+  if (!__any_sync(kFullMask, want)) return false;
+  bool done = !want, ok = false;
+  for (int it = 0; it < 30 && __any_sync(kFullMask, !done); ++it) {
     const float mid = lo + (hi - lo) * 0.5f;
     int cgt = 0;
+#pragma unroll 8
+    for (int i = 0; i < maxcnt; ++i) cgt += (__uint_as_float(ld_shared_b32(s_addr + i * kSlotStride)) > mid) ? 1 : 0;
     uint32_t ra[32], rb[32];
     tmem_ld_32x32b_x32(tile_addr, ra);
 #pragma unroll 1
@@ -433,9 +456,24 @@ __device__ __noinline__ float tile_bound_by_bisection(uint32_t tile_addr, bool e
       }
     }
   }
-  // lo itself is not a score: "score > lo" admits exactly the c_lo scores counted.  The caller stores pred(bound), so hand
-  // back the next float above lo.
-  return (want && ok) ? ordered_to_float(float_to_ordered(lo) + 1u) : kNegInf;
+  const bool part = want && ok;
+  if (__any_sync(kFullMask, part)) {
+    int w = 0;
+#pragma unroll 4
+    for (int i = 0; i < maxcnt; ++i) {
+      const uint32_t v = ld_shared_b32(s_addr + i * kSlotStride);
+      const uint32_t c = ld_shared_b32(c_addr + i * kSlotStride);
+      const bool keep = part && (__uint_as_float(v) > lo);
+      st_shared_b32_pred(s_addr + w * kSlotStride, v, keep);
+      st_shared_b32_pred(c_addr + w * kSlotStride, c, keep);
+      w += keep ? 1 : 0;
+    }
+    if (part) {
+      cnt = w;
+      thr = lo;
+    }
+  }
+  return true;
 }
 
 // Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
@@ -590,7 +628,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t wbase = smem_u32(smem + L.keys_off) + static_cast<uint32_t>(quarter) * (CAP * 2 * kSlotStride);
     const uint32_t s_addr = wbase + static_cast<uint32_t>(lane) * 4u;     // score word, slot 0 of this thread's own row
     const uint32_t c_addr = s_addr + CAP * kSlotStride;                    // column word, slot 0
-    const int target_hi = compaction_target(CAP, p.kprime);
+    const int target_hi = p.target_hi;
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
@@ -604,6 +642,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const bool valid = qrow < p.Q;
       float thr = valid ? kNegInf : kPosInf;
       int cnt = 0;
+      bool joint_next = false;                  // warp-uniform: bound the next tile jointly before collecting it
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1;
         // pick up what other CTAs (and earlier strips) have learnt about this row while the MMAs finish
@@ -623,13 +662,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const uint32_t tile_addr = tmem_base + lane_base + buf * kTileN;
         if constexpr (!kDense) {
           // Cold start: a row about which nothing is known yet (thr = -inf) would push every score of its first tile through
-          // the candidate buffer.  Instead the tile is read a few more times to find a bound that admits only a few more
-          // than K' of its scores (a valid lower bound of the row's K'-th best: K' scores of the row lie above it).
-          if (__any_sync(kFullMask, valid && thr == kNegInf)) {
-            float bound = kNegInf;
-            if constexpr (CAP == 64) {
-              // K' <= 32: the K'-th largest of the tile's 32 group maxima (8 columns each) -- one extra read of the tile and
-              // a per-thread sorting network; admits ~8 % of the tile.
+          // the candidate buffer; and while a row is young, scores above its bound arrive faster than a compaction frees
+          // slots.  In both cases the tile is read a few more times FIRST, to find a bound that admits only as many scores
+          // as the buffer can take (a valid lower bound of the row's K'-th best: K' known scores of the row lie above it).
+          const bool any_cold = __any_sync(kFullMask, valid && thr == kNegInf);
+          if (any_cold || joint_next) {
+            const int ncols = edge ? static_cast<int>(p.N - col_tile) : kTileN;
+            bool tightened = false;
+            if (CAP == 64 && !joint_next) {
+              // K' <= 32, first tile: the K'-th largest of the tile's 32 group maxima (8 columns each) -- one extra read of
+              // the tile and a per-thread sorting network; admits ~8 % of the tile.
               float gmx[32];
 #pragma unroll
               for (int c = 0; c < kTileN / 32; ++c) {
@@ -642,25 +684,26 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const float x = __uint_as_float(raw[8 * g + j]);
-                    const bool in_range = !edge || (col_tile + c * 32 + 8 * g + j < p.N);
-                    mx = in_range ? fmaxf(mx, x) : mx;
+                    mx = (c * 32 + 8 * g + j < ncols) ? fmaxf(mx, x) : mx;
                   }
                   gmx[4 * c + g] = (mx == mx) ? mx : kNegInf;
                 }
               }
               thread_sort_desc<32>(gmx);
-              bound = gmx[0];
+              float bound = gmx[0];
 #pragma unroll
               for (int i = 1; i < 32; ++i) bound = (i == p.kprime - 1) ? gmx[i] : bound;
+              if (valid && thr == kNegInf && bound > kNegInf) {
+                publish_threshold(p, qrow, bound);
+                thr = pred_float(bound);                                 // admit scores equal to the bound
+              }
+              tightened = true;
             } else {
-              // longer lists: bisection on the score value, counting the tile's scores above the midpoint (thread <-> row:
-              // no shuffles), until between K' and target_hi of them lie above it
-              bound = tile_bound_by_bisection(tile_addr, edge, col_tile, p.N, p.kprime, target_hi, valid && thr == kNegInf);
+              const float before = thr;
+              tightened = joint_bound(tile_addr, ncols, s_addr, c_addr, p.kprime, target_hi, valid, cnt, thr);
+              if (valid && thr != before) publish_threshold(p, qrow, thr);
             }
-            if (valid && thr == kNegInf && bound > kNegInf) {
-              publish_threshold(p, qrow, bound);
-              thr = pred_float(bound);                                 // admit scores equal to the bound
-            }
+            joint_next = tightened && p.joint_after > 0;
           }
         }
         if constexpr (kDense) {
@@ -713,14 +756,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
 #endif
           }
-          // ---- pass 2 (collect): only the chunks that were hit are read again and appended from
-#pragma unroll 1
-          while (hit) {
-            const int c = __ffs(hit) - 1;
-            hit &= hit - 1;
-            uint32_t raw[32];
-            tmem_ld_32x32b_x32(tile_addr + c * 32, raw);
-            tmem_ld_wait();
+          // ---- pass 2 (collect): only the chunks that were hit are read again (next hit chunk in flight while the current
+          // one is appended from)
+          int compactions = 0;
+          auto collect_chunk = [&](int c, const uint32_t (&raw)[32]) {
             const int64_t col0 = col_tile + c * 32;
             float v[32];
 #pragma unroll
@@ -740,7 +779,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
-              if (__any_sync(kFullMask, cnt > CAP - 8)) {
+              if (__any_sync(kFullMask, cnt > p.trig_level)) {
                 // some row is (nearly) full: every row of the warp that holds more than K' entries sheds its tail
                 const float before = thr;
                 const uint32_t failed = compact_local(s_addr, c_addr, p.kprime, target_hi, cnt, thr);
@@ -750,6 +789,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                   thr = st.thr;
                 }
                 if (thr != before) publish_threshold(p, qrow, thr);
+                ++compactions;
               }
               // branch-free appends: score bits and ~column stored under a predicate
               const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
@@ -763,7 +803,35 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 cnt += take ? 1 : 0;
               }
             }
+          };
+          if (hit) {
+            uint32_t ra[32], rb[32];
+            int ca = __ffs(hit) - 1, cb = -1;
+            hit &= hit - 1;
+            tmem_ld_32x32b_x32(tile_addr + ca * 32, ra);
+#pragma unroll 1
+            while (true) {
+              tmem_ld_wait();
+              cb = -1;
+              if (hit) {
+                cb = __ffs(hit) - 1;
+                hit &= hit - 1;
+                tmem_ld_32x32b_x32(tile_addr + cb * 32, rb);
+              }
+              collect_chunk(ca, ra);
+              if (cb < 0) break;
+              tmem_ld_wait();
+              ca = -1;
+              if (hit) {
+                ca = __ffs(hit) - 1;
+                hit &= hit - 1;
+                tmem_ld_32x32b_x32(tile_addr + ca * 32, ra);
+              }
+              collect_chunk(cb, rb);
+              if (ca < 0) break;
+            }
           }
+          if (p.joint_after > 0 && compactions >= p.joint_after) joint_next = true;
         }
         // every score of the tile has been looked at: hand the TMEM buffer back to the MMA issuer
         tc_fence_before();
@@ -950,10 +1018,14 @@ int launch_fused(const CUtensorMap& tq, const CUtensorMap& tc, const FusedParams
                  cudaStream_t stream) {
   const SmemLayout L = smem_layout(p.stages, kDense ? 0 : CAP, kCta, p.a_rows, p.key_warps);
   auto kern = fused_score_topk_kernel<CAP, kF8, kDense, kCta>;
-  static bool attr_set = false;   // one per template instantiation
-  if (!attr_set) {
+  // the attribute is per device (context): one bit per device ordinal, one mask per template instantiation
+  static std::atomic<unsigned long long> attr_done{0ull};
+  int dev = 0;
+  MMD_CUDA_OK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if ((attr_done.load(std::memory_order_acquire) & bit) == 0ull) {
     MMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool profiled = false, capturing = false;
@@ -1158,6 +1230,17 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = sch.T; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = k;
   p.a_rows = a_rows; p.key_warps = key_warps;
+  {
+    // tuning knobs of the candidate-buffer maintenance (env overrides for sweeps; defaults from measurements)
+    static const int win = [] { const char* e = getenv("MMD_WINDOW"); return e ? atoi(e) : 4; }();
+    static const int trig = [] { const char* e = getenv("MMD_TRIGGER"); return e ? atoi(e) : 0; }();      // 0 = when < 8 slots are free
+    static const int joint = [] { const char* e = getenv("MMD_JOINT_AFTER"); return e ? atoi(e) : 2; }();
+    p.target_hi = compaction_target(cap, k, win < 0 ? 0 : win);
+    p.trig_level = cap - 8;
+    if (trig > 0 && k + trig < p.trig_level) p.trig_level = k + trig;
+    if (p.trig_level < p.target_hi) p.trig_level = p.target_hi;          // (a compaction must be able to get below the trigger)
+    p.joint_after = joint;
+  }
   p.stages = stages_for(cap, cta, a_rows, key_warps);
   p.partial = static_cast<uint64_t*>(workspace);
   if (thr_local == nullptr) {

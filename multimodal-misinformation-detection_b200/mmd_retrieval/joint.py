@@ -94,6 +94,13 @@ def prepare_joint(corpora: Sequence, weights: Optional[Sequence[float]] = None, 
     w = [1.0 / len(corpora)] * len(corpora) if weights is None else [float(x) for x in weights]
     if len(w) != len(corpora) or any(x < 0 for x in w):
         raise ValueError("one non-negative weight per modality")
+    if dtype == "fp8":
+        # e4m3 operands carry a fixed 2^8 scale sized for |x| <= 1 (unit-norm rows; the query side is also multiplied by w_m):
+        # 256 * 1.75 = 448 is the largest finite e4m3 value
+        if metric != "cos":
+            raise ValueError("dtype='fp8' needs metric='cos' (unit-norm operands)")
+        if any(x > 1.75 for x in w):
+            raise ValueError("dtype='fp8' needs modality weights <= 1.75 (the scaled query operands would saturate e4m3)")
     if device is not None:
         dev = torch.device(device)
     elif isinstance(corpora[0], torch.Tensor) and corpora[0].is_cuda:

@@ -123,6 +123,10 @@ def prepare_corpus(corpus, dtype: str = "bf16", metric: str = "cos", eps: float 
         raise ValueError(f"dtype must be one of {sorted(_OP_DTYPE)}, got {dtype!r}")
     if metric not in METRICS:
         raise ValueError(f"metric must be one of {METRICS}, got {metric!r}")
+    if dtype == "fp8" and metric == "dot":
+        # the e4m3 operands carry a fixed 2^8 scale that assumes unit-norm rows (|x| <= 1); un-normalised embeddings would
+        # saturate at 448 or underflow and the candidate selection would silently be garbage
+        raise ValueError("dtype='fp8' needs metric='cos' (unit-norm operands); use bf16 / fp16 / fp32 for inner-product scoring")
     if device is not None:
         dev = torch.device(device)
     elif isinstance(corpus, torch.Tensor) and corpus.is_cuda:
@@ -146,7 +150,13 @@ def max_k() -> int:
 def overfetch_for(k: int, n: int) -> int:
     """Candidates kept by the low-precision pass when an exact re-score follows: k + max(8, k/2), but never so
     many that the per-row candidate buffer of the fused kernel (128 entries for lists longer than 32) is left
-    with fewer than 24 free slots between two compactions."""
+    with fewer than 24 free slots between two compactions.
+
+    CAVEAT (k > 69): the cap of 104 shrinks the over-fetch -- at the reference's largest list, k = 100
+    (experiment_text.py:26), only 4 spare candidates are re-scored.  bf16 operand noise is ~1e-4 absolute; on corpora large
+    enough that the rank-k score spacing falls below that (~1e-4 at rank 100 of a 1M-row Gaussian corpus; the reference's
+    own corpora hold 7.5k / 35k rows, spacing ~1e-3) a true top-k row whose bf16 score ranks below K' is never re-scored.
+    tests/test_gpu_fullsize.py states the measured recall@100 on 1M rows; dtype="fp32" (6-term bf16 split) is exact."""
     return max(1, min(n, max(k, min(k + max(8, k // 2), 104)), max_k()))
 
 
@@ -164,9 +174,10 @@ def topk_prepared(q_rows: torch.Tensor, n_queries: int, corpus: PreparedCorpus, 
     if n_queries == 0:
         return scores, idx
     op = _OP_DTYPE[corpus.op]
-    ws_bytes = int(lib.mmd_topk_workspace_bytes(n_queries, max(corpus.n, 1), corpus.dim, op, k))
-    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
+        # (inside the device guard: the schedule the workspace is sized for depends on the SM count of the device that runs it)
+        ws_bytes = int(lib.mmd_topk_workspace_bytes(n_queries, max(corpus.n, 1), corpus.dim, op, k))
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
         if shared_thr is None:
             rc = lib.mmd_topk_scores(_ptr(q_rows), _ptr(corpus.rows), op, n_queries, corpus.n, corpus.dim, k, corpus.idx_offset,
                                      _ptr(scores), _ptr(idx), _ptr(ws), ws_bytes, _stream_ptr(dev))

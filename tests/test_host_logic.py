@@ -84,3 +84,54 @@ def test_ordered_bound_matches_the_kernel_threshold_encoding():
     s = torch.tensor([-2.0, -1.0, -0.5, 0.0, 0.25, 1.0])
     b = ops._ordered_bound(s, 65536.0)
     assert bool((b[1:] > b[:-1]).all()) and b.tolist() == [device_encoding(float(v) * 65536.0) for v in s]
+
+
+def test_fp8_needs_unit_norm_operands():
+    """e4m3 operands carry a fixed 2^8 scale sized for |x| <= 1: inner-product scoring of un-normalised rows and modality
+    weights above 1.75 are refused up front -- before any device is touched."""
+    with pytest.raises(ValueError, match="fp8"):
+        m.prepare_corpus(torch.ones(3, 16), dtype="fp8", metric="dot")
+    with pytest.raises(ValueError, match="fp8"):
+        m.prepare_joint([torch.ones(3, 16), torch.ones(3, 16)], weights=(0.5, 0.5), dtype="fp8", metric="dot")
+    with pytest.raises(ValueError, match="1.75"):
+        m.prepare_joint([torch.ones(3, 16), torch.ones(3, 16)], weights=(2.0, 0.5), dtype="fp8")
+
+
+class _FakeShard:
+    """Just enough of a PreparedCorpus for the host-side planning code (no device memory)."""
+    source = object()
+    n, dim, op, metric, eps, idx_offset = 125_000, 768, "bf16", "cos", 1e-12, 0
+    rows = torch.empty((0, 1536), dtype=torch.uint8)
+    device = torch.device("cpu")
+
+
+def test_sharded_step_planning():
+    """Sub-batch split (whole 256-query tiles, sums to Q), exchanged list widths, and the layout of the symmetric ring."""
+    sc = sharded.ShardedCorpus(None, 1_000_000, 0, _shard=_FakeShard())
+    assert sc._sub_sizes(16384) == [16384] and sc._sub_sizes(1) == [1] and sc._sub_sizes(0) == []
+    sc.sub_batches = 2
+    assert sc._sub_sizes(16384) == [8192, 8192] and sc._sub_sizes(300) == [256, 44] and sc._sub_sizes(256) == [256]
+    sc.sub_batches = 5
+    for q in (1, 255, 257, 1000, 16384, 65536):
+        sizes = sc._sub_sizes(q)
+        assert sum(sizes) == q and all(s % 256 == 0 for s in sizes[:-1]) and len(sizes) <= 5
+    # (k_glob, K' every rank exchanges, global candidate list): a single rank re-scores all K'
+    assert sc._widths(10) == (10, 18, 18) and sc._widths(100) == (100, 104, 104)
+    sc.world, sc._max_local, sc._min_local, sc.n_total = 4, 11, 10, 41           # 41 rows over 4 ranks
+    assert sc._widths(10) == (10, 11, 18)                                          # lists shorter than the global candidate list
+    sc.n_total, sc._max_local = 5, 2
+    assert sc._widths(10) == (5, 2, 5)
+
+
+def test_compaction_target_leaves_room_for_the_pending_appends():
+    """Mirror of compaction_target() in csrc/topk_fused.cu: a compaction must leave at most CAP - 16 entries (8 slots for the
+    group of appends that triggered it) whenever K' allows, and never fewer than K'."""
+    def target(cap, kprime):
+        slack = max((cap - kprime) // 3, 8)
+        want, most = kprime + slack, cap - 16
+        return want if want < most else (most if most > kprime else kprime)
+    for cap, ks in ((64, range(1, 33)), (128, range(33, 121))):
+        for k in ks:
+            t = target(cap, k)
+            assert k <= t and (t <= cap - 16 or t == k)
+    assert target(64, 18) == 33 and target(128, 104) == 112 and target(128, 120) == 120
