@@ -41,10 +41,6 @@ int fill_arrive(PeerArrive* a, void* const* flags_host, int n, uint32_t* state, 
 
 namespace {
 
-#ifndef MMD_FILTER_W
-#define MMD_FILTER_W 64             // columns per tcgen05.ld in the epilogue's filter pass (32 or 64)
-#endif
-
 constexpr int kTileM = 128;          // queries per tile  (UMMA M, TMEM lanes)
 constexpr int kTileN = 256;          // corpus rows per tile (UMMA N, TMEM columns)
 constexpr int kBlockKBytes = 128;    // one swizzle atom along K per stage
@@ -69,9 +65,6 @@ struct FusedParams {
   int stages;
   int a_rows;            // query rows staged per CTA and K block: 128, or the 32-row groups a batch of < 128 queries fills
   int key_warps;         // epilogue warps (lane quarters 0 .. key_warps-1) that own candidate buffers: a_rows / 32
-  int trig_level;        // a row holding more than this many candidates triggers a compaction of the warp's rows
-  int target_hi;         // a compaction leaves between kprime and this many candidates in a row
-  int joint_after;       // compactions within one tile after which the next tile is bounded jointly up front (0 = never)
   uint64_t* partial;     // [Q][S][kprime] keys
   uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
   uint32_t* thr_peer[8]; // row-sharded corpus: the same array on EVERY rank (peer-mapped, own one included); a bound
@@ -112,93 +105,22 @@ __host__ __device__ inline SmemLayout smem_layout(int stages, int cap, int cta, 
   return l;
 }
 
-// ---------------------------------------------------------------- per-row candidate buffers
-// An epilogue warp owns 32 query rows (lane = row).  A row's buffer has CAP slots, structure-of-arrays in shared memory:
-//   score word of slot s (raw fp32 bits): wbase + s * 128 + lane * 4
-//   column word of slot s (~column):      wbase + CAP * 128 + s * 128 + lane * 4
-// so every access a thread makes to ITS OWN row is bank-conflict free for any mix of per-row counts, and an append is two
-// predicated 4-byte stores.  The buffers stay UNSORTED while a unit runs; two routines keep them small:
-//   * compact_local  (the common case)  every thread works on its own row, all 32 rows at once: bisection on the score
-//     value, counting "entries > mid" with plain loads, finds a threshold tau with K' <= count(> tau) <= target; entries
-//     <= tau are dropped by an in-place partition and tau becomes the row's bound.  No shuffles, no sort: ~3 instructions
-//     per entry and pass for 32 rows together (the round-1 warp-wide bitonic re-sort cost ~1.2-2.5 k cycles PER ROW).
-//   * compact_rows   (fallback + end of unit)  warp-cooperative bitonic sort of one row at a time: rows whose bisection
-//     cannot converge (more equal scores around the K'-th best than the slack holds -- duplicate-heavy corpora), and the
-//     final sorted K'-list every unit hands to the strip merge.
-constexpr uint32_t kSlotStride = 128;
-constexpr uint32_t kNegInfBits = 0xff800000u;
-
-__device__ __forceinline__ float pred_float(float x) { return ordered_to_float(float_to_ordered(x) - 1u); }
-__device__ __forceinline__ uint64_t raw_to_key(uint32_t score_bits, uint32_t colword) {
-  return (static_cast<uint64_t>(float_to_ordered(__uint_as_float(score_bits))) << 32) | colword;
+// ---------------------------------------------------------------- warp-cooperative list maintenance
+// Candidate (slot, row r of this warp) lives at wkeys[slot * 32 + r], as a RAW entry {lo = ~column, hi = fp32 score bits}:
+// an append is then four instructions (compare, address, predicated 8-byte store, predicated count) with no
+// bank conflicts for any mix of per-row counts (slots are 256 B apart, a multiple of the 128 B bank cycle).  Entries
+// become ordered keys only when a row is compacted; the warp-wide read of one row there is a 32-way bank conflict,
+// paid twice per compaction instead of once per appended score.
+__device__ __forceinline__ int key_slot_index(int slot, int r) { return slot * 32 + r; }
+__device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) {
+  return raw == 0ull ? 0ull
+                     : (static_cast<uint64_t>(float_to_ordered(__uint_as_float(static_cast<uint32_t>(raw >> 32)))) << 32) |
+                           (raw & 0xffffffffull);
 }
-
-// Largest entry count a compaction may leave behind: K' plus a small window (a wider window converges in fewer passes but
-// leaves a looser bound, and the bound is what keeps the collect pass rare), always at least 16 free slots.
-__host__ __device__ constexpr int compaction_target(int cap, int kprime, int window) {
-  const int want = kprime + window;
-  const int most = cap - 16;
-  return want < most ? want : (most > kprime ? most : kprime);
-}
-
-// All lanes call it.  Rows holding more than K' entries are compacted; returns the ballot of rows that did NOT converge
-// (their buffers are untouched).  cnt / thr are the calling lane's own row state.
-__device__ __noinline__ uint32_t compact_local(uint32_t s_addr, uint32_t c_addr, int kprime, int target_hi, int& cnt, float& thr) {
-  const float kNegInf = __uint_as_float(kNegInfBits);
-  const float kPosInf = __uint_as_float(0x7f800000u);
-  const bool active = cnt > kprime;
-  const int maxcnt = __reduce_max_sync(kFullMask, active ? cnt : 0);
-  if (maxcnt == 0) return 0u;
-  // pass 0: min / max of the own entries; slots [cnt, maxcnt) are padded with -inf so that the counting passes need no mask
-  float mn = kPosInf, mx = kNegInf;
-#pragma unroll 4
-  for (int i = 0; i < maxcnt; ++i) {
-    const float v = __uint_as_float(ld_shared_b32(s_addr + i * kSlotStride));
-    const bool own = i < cnt;
-    st_shared_b32_pred(s_addr + i * kSlotStride, kNegInfBits, !own);
-    mn = fminf(mn, own ? v : kPosInf);
-    mx = fmaxf(mx, own ? v : kNegInf);
-  }
-  // invariant: count(> lo) = c_lo >= K'  and  count(> hi) < K'
-  float lo = fmaxf(thr, pred_float(mn)), hi = mx;
-  int c_lo = cnt;
-  bool done = !active || c_lo <= target_hi;
-  bool ok = done;
-  for (int it = 0; it < 28 && __any_sync(kFullMask, !done); ++it) {
-    const float mid = lo + (hi - lo) * 0.5f;
-    int c = 0;
-#pragma unroll 8
-    for (int i = 0; i < maxcnt; ++i) c += (__uint_as_float(ld_shared_b32(s_addr + i * kSlotStride)) > mid) ? 1 : 0;
-    if (!done) {
-      if (!(mid > lo && mid < hi)) {
-        done = true;                       // adjacent floats: equal scores straddle the K'-th best -> sort fallback
-      } else if (c >= kprime) {
-        lo = mid;
-        c_lo = c;
-        done = ok = c <= target_hi;
-      } else {
-        hi = mid;
-      }
-    }
-  }
-  const bool part = active && ok;
-  if (__any_sync(kFullMask, part)) {
-    int w = 0;
-#pragma unroll 4
-    for (int i = 0; i < maxcnt; ++i) {
-      const uint32_t v = ld_shared_b32(s_addr + i * kSlotStride);
-      const uint32_t c = ld_shared_b32(c_addr + i * kSlotStride);
-      const bool keep = part && (__uint_as_float(v) > lo);
-      st_shared_b32_pred(s_addr + w * kSlotStride, v, keep);
-      st_shared_b32_pred(c_addr + w * kSlotStride, c, keep);
-      w += keep ? 1 : 0;
-    }
-    if (part) {
-      cnt = w;
-      thr = lo;                            // >= the old bound; at least K' entries of this row are above it
-    }
-  }
-  return __ballot_sync(kFullMask, active && !ok);
+__device__ __forceinline__ uint64_t key_to_raw(uint64_t key) {
+  return key == 0ull ? 0ull
+                     : (static_cast<uint64_t>(__float_as_uint(ordered_to_float(static_cast<uint32_t>(key >> 32)))) << 32) |
+                           (key & 0xffffffffull);
 }
 
 // R rows at a time go through the same bitonic network (independent dependency chains: one epilogue warp per
@@ -249,25 +171,24 @@ struct RowState {
   float thr;
 };
 
-// Sort the candidate buffers of the rows named in `rows` (R at a time); keep the best `kprime` by (score desc, column asc).
-//   FINAL = false : write the survivors back (the row then holds exactly min(n, kprime) entries).
+// Sort the candidate buffers of the rows named in `mask` (R of them at a time); keep the best `kprime`.
+//   FINAL = false : write the survivors back.
 //   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
-// (The warp-wide read of one row is a 32-way bank conflict; this path is rare -- see above.)
+// Returns the calling lane's own (count, threshold): a compacted row holds min(n, kprime) entries and, once it
+// holds kprime, its threshold is at least its kprime-th best score.
 template <int CAP, bool FINAL, int R, int E>
-__device__ __forceinline__ void compact_batch(uint32_t wbase, const int (&rows)[R], int lane, int kprime, int& cnt,
+__device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int& cnt,
                                               float& thr, uint64_t* out_rows, int64_t out_row_stride) {
+  // E = registers per lane and row (CAP / 32)
   uint64_t k[R][E];
   int n[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     n[r] = __shfl_sync(kFullMask, cnt, rows[r]);
-    const uint32_t base = wbase + rows[r] * 4;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = e * 32 + lane;
-      k[r][e] = 0ull;
-      if (i < n[r])
-        k[r][e] = raw_to_key(ld_shared_b32(base + i * kSlotStride), ld_shared_b32(base + CAP * kSlotStride + i * kSlotStride));
+      k[r][e] = (i < n[r]) ? raw_to_key(wkeys[key_slot_index(i, rows[r])]) : 0ull;
     }
   }
   bitonic_sort_desc<E, R>(k, lane);
@@ -276,14 +197,10 @@ __device__ __forceinline__ void compact_batch(uint32_t wbase, const int (&rows)[
   for (int r = 0; r < R; ++r) {
     const int keep = n[r] < kprime ? n[r] : kprime;
     if constexpr (!FINAL) {
-      const uint32_t base = wbase + rows[r] * 4;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;
-        if (i < keep) {
-          st_shared_b32(base + i * kSlotStride, __float_as_uint(key_score(k[r][e])));
-          st_shared_b32(base + CAP * kSlotStride + i * kSlotStride, static_cast<uint32_t>(k[r][e]));
-        }
+        if (i < keep) wkeys[key_slot_index(i, rows[r])] = key_to_raw(k[r][e]);
       }
     } else {
       uint64_t* out = out_rows + static_cast<int64_t>(rows[r]) * out_row_stride;
@@ -305,7 +222,7 @@ __device__ __forceinline__ void compact_batch(uint32_t wbase, const int (&rows)[
 }
 
 template <int CAP, bool FINAL>
-__device__ __noinline__ RowState compact_rows(uint32_t wbase, uint32_t mask, int lane, int kprime, int cnt, float thr,
+__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int cnt, float thr,
                                               uint64_t* out_rows, int64_t out_row_stride) {
   constexpr int R = CAP == 64 ? 4 : 2;
   constexpr int E = CAP / 32;
@@ -317,13 +234,13 @@ __device__ __noinline__ RowState compact_rows(uint32_t wbase, uint32_t mask, int
       rows[r] = __ffs(mask) - 1;
       mask &= mask - 1;
     }
-    compact_batch<CAP, FINAL, R, E>(wbase, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+    compact_batch<CAP, FINAL, R, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
   }
   while (mask) {
     int rows[1];
     rows[0] = __ffs(mask) - 1;
     mask &= mask - 1;
-    compact_batch<CAP, FINAL, 1, E>(wbase, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+    compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
   }
   __syncwarp();
   RowState st;
@@ -355,125 +272,13 @@ __device__ __forceinline__ void thread_sort_desc(float (&v)[N]) {
 }
 
 // Maximum of the 32 scores one tcgen05.ld delivered (3-input maxima on sm_100).
-__device__ __forceinline__ float chunk_max(const uint32_t* r) {
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
   float m[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
                  fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-}
-
-// Joint bound of (a row's candidate buffer + the accumulator tile that is about to be collected), found BEFORE the tile is
-// collected: tau such that between K' and target_hi of {buffer entries, tile scores} lie above it.  The buffer is then
-// partitioned by tau in place and tau becomes the row's bound, so the collect pass that follows appends at most
-// target_hi - (entries kept) scores and never overflows.  Used where scores arrive faster than a compaction frees slots:
-// the first tiles of a cold row (thr = -inf; for K' > 32 this replaces the group-maxima trick) and any tile that follows
-// one with several compactions.  Bisection on the score value; a pass counts buffer entries (shared memory) and tile
-// scores (TMEM, double-buffered 32-column loads) above the midpoint -- thread <-> row, no shuffles.  Rows that do not need
-// it (fewer than target_hi + 1 scores above their bound), rows without K' scores yet, and rows whose bisection cannot
-// converge (equal scores straddling the K'-th best) are left alone; the regular collect + compaction handles them.
-// Returns true (warp-uniform) if any row needed tightening.
-__device__ __noinline__ bool joint_bound(uint32_t tile_addr, int ncols, uint32_t s_addr, uint32_t c_addr, int kprime, int target_hi,
-                                         bool valid, int& cnt, float& thr) {
-  const float kNegInf = __uint_as_float(kNegInfBits);
-  const float kPosInf = __uint_as_float(0x7f800000u);
-  const int maxcnt = __reduce_max_sync(kFullMask, valid ? cnt : 0);
-  float mn = kPosInf, mx = kNegInf;
-#pragma unroll 4
-  for (int i = 0; i < maxcnt; ++i) {
-    const float v = __uint_as_float(ld_shared_b32(s_addr + i * kSlotStride));
-    const bool own = i < cnt;
-    st_shared_b32_pred(s_addr + i * kSlotStride, kNegInfBits, !own);
-    mn = fminf(mn, own ? v : kPosInf);
-    mx = fmaxf(mx, own ? v : kNegInf);
-  }
-  int nvalid = 0, above = 0;
-  {
-    uint32_t ra[32], rb[32];
-    tmem_ld_32x32b_x32(tile_addr, ra);
-#pragma unroll 1
-    for (int c = 0; c < kTileN / 32; c += 2) {
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, rb);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(ra[j]);
-        const bool ok = (c * 32 + j < ncols) && (x == x);
-        mn = fminf(mn, ok ? x : kPosInf);
-        mx = fmaxf(mx, ok ? x : kNegInf);
-        nvalid += ok ? 1 : 0;
-        above += (ok && x > thr) ? 1 : 0;
-      }
-      tmem_ld_wait();
-      if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(tile_addr + (c + 2) * 32, ra);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(rb[j]);
-        const bool ok = ((c + 1) * 32 + j < ncols) && (x == x);
-        mn = fminf(mn, ok ? x : kPosInf);
-        mx = fmaxf(mx, ok ? x : kNegInf);
-        nvalid += ok ? 1 : 0;
-        above += (ok && x > thr) ? 1 : 0;
-      }
-    }
-  }
-  // invariant: count(> lo) = c_lo >= K'  and  count(> hi) < K'   (counts over buffer + tile)
-  const bool cold = !(thr > kNegInf);
-  float lo = cold ? pred_float(mn) : thr;
-  int c_lo = cold ? cnt + nvalid : cnt + above;
-  float hi = mx;
-  const bool want = valid && c_lo > target_hi;
-  if (!__any_sync(kFullMask, want)) return false;
-  bool done = !want, ok = false;
-  for (int it = 0; it < 30 && __any_sync(kFullMask, !done); ++it) {
-    const float mid = lo + (hi - lo) * 0.5f;
-    int cgt = 0;
-#pragma unroll 8
-    for (int i = 0; i < maxcnt; ++i) cgt += (__uint_as_float(ld_shared_b32(s_addr + i * kSlotStride)) > mid) ? 1 : 0;
-    uint32_t ra[32], rb[32];
-    tmem_ld_32x32b_x32(tile_addr, ra);
-#pragma unroll 1
-    for (int c = 0; c < kTileN / 32; c += 2) {
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, rb);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) cgt += ((c * 32 + j < ncols) && (__uint_as_float(ra[j]) > mid)) ? 1 : 0;
-      tmem_ld_wait();
-      if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(tile_addr + (c + 2) * 32, ra);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) cgt += (((c + 1) * 32 + j < ncols) && (__uint_as_float(rb[j]) > mid)) ? 1 : 0;
-    }
-    if (!done) {
-      if (!(mid > lo && mid < hi)) {
-        done = true;
-      } else if (cgt >= kprime) {
-        lo = mid;
-        c_lo = cgt;
-        done = ok = cgt <= target_hi;
-      } else {
-        hi = mid;
-      }
-    }
-  }
-  const bool part = want && ok;
-  if (__any_sync(kFullMask, part)) {
-    int w = 0;
-#pragma unroll 4
-    for (int i = 0; i < maxcnt; ++i) {
-      const uint32_t v = ld_shared_b32(s_addr + i * kSlotStride);
-      const uint32_t c = ld_shared_b32(c_addr + i * kSlotStride);
-      const bool keep = part && (__uint_as_float(v) > lo);
-      st_shared_b32_pred(s_addr + w * kSlotStride, v, keep);
-      st_shared_b32_pred(c_addr + w * kSlotStride, c, keep);
-      w += keep ? 1 : 0;
-    }
-    if (part) {
-      cnt = w;
-      thr = lo;
-    }
-  }
-  return true;
 }
 
 // Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
@@ -625,10 +430,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     // candidate buffers are indexed by the lane quarter (= 32-row group of the tile); with key_warps = 1 only quarter 0
     // (query rows 0..31) owns one -- the other warps' rows are all beyond Q and never touch theirs
-    const uint32_t wbase = smem_u32(smem + L.keys_off) + static_cast<uint32_t>(quarter) * (CAP * 2 * kSlotStride);
-    const uint32_t s_addr = wbase + static_cast<uint32_t>(lane) * 4u;     // score word, slot 0 of this thread's own row
-    const uint32_t c_addr = s_addr + CAP * kSlotStride;                    // column word, slot 0
-    const int target_hi = p.target_hi;
+    uint64_t* wkeys = reinterpret_cast<uint64_t*>(smem + L.keys_off) + static_cast<size_t>(quarter) * (CAP * 32);
+    const uint32_t row_addr = smem_u32(wkeys) + static_cast<uint32_t>(lane) * 8u;   // slot 0 of this thread's own row
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
@@ -642,7 +445,6 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const bool valid = qrow < p.Q;
       float thr = valid ? kNegInf : kPosInf;
       int cnt = 0;
-      bool joint_next = false;                  // warp-uniform: bound the next tile jointly before collecting it
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1;
         // pick up what other CTAs (and earlier strips) have learnt about this row while the MMAs finish
@@ -659,58 +461,45 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         const int64_t col_tile = static_cast<int64_t>(t) * kTileN;
         const bool edge = col_tile + kTileN > p.N;
-        const uint32_t tile_addr = tmem_base + lane_base + buf * kTileN;
-        if constexpr (!kDense) {
-          // Cold start: a row about which nothing is known yet (thr = -inf) would push every score of its first tile through
-          // the candidate buffer; and while a row is young, scores above its bound arrive faster than a compaction frees
-          // slots.  In both cases the tile is read a few more times FIRST, to find a bound that admits only as many scores
-          // as the buffer can take (a valid lower bound of the row's K'-th best: K' known scores of the row lie above it).
-          const bool any_cold = __any_sync(kFullMask, valid && thr == kNegInf);
-          if (any_cold || joint_next) {
-            const int ncols = edge ? static_cast<int>(p.N - col_tile) : kTileN;
-            bool tightened = false;
-            if (CAP == 64 && !joint_next) {
-              // K' <= 32, first tile: the K'-th largest of the tile's 32 group maxima (8 columns each) -- one extra read of
-              // the tile and a per-thread sorting network; admits ~8 % of the tile.
-              float gmx[32];
+        if constexpr (!kDense && CAP == 64) {
+          // Cold start: a row about which nothing is known yet (thr = -inf) would push every score of its first
+          // tile through the candidate buffer (one warp-wide sort per ~40 scores).  Instead, read the tile once
+          // more: the K'-th largest of its 32 group maxima (8 columns each) is K' distinct scores of this row,
+          // hence a lower bound of the row's K'-th best; it admits ~8 % of the tile.
+          if (__any_sync(kFullMask, valid && thr == kNegInf)) {
+            float gmx[32];
 #pragma unroll
-              for (int c = 0; c < kTileN / 32; ++c) {
-                uint32_t raw[32];
-                tmem_ld_32x32b_x32(tile_addr + c * 32, raw);
-                tmem_ld_wait();
+            for (int c = 0; c < kTileN / 32; ++c) {
+              uint32_t raw[32];
+              tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+              tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float mx = kNegInf;
+              for (int g = 0; g < 4; ++g) {
+                float mx = kNegInf;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float x = __uint_as_float(raw[8 * g + j]);
-                    mx = (c * 32 + 8 * g + j < ncols) ? fmaxf(mx, x) : mx;
-                  }
-                  gmx[4 * c + g] = (mx == mx) ? mx : kNegInf;
+                for (int j = 0; j < 8; ++j) {
+                  const float x = __uint_as_float(raw[8 * g + j]);
+                  const bool in_range = !edge || (col_tile + c * 32 + 8 * g + j < p.N);
+                  mx = in_range ? fmaxf(mx, x) : mx;
                 }
+                gmx[4 * c + g] = (mx == mx) ? mx : kNegInf;
               }
-              thread_sort_desc<32>(gmx);
-              float bound = gmx[0];
-#pragma unroll
-              for (int i = 1; i < 32; ++i) bound = (i == p.kprime - 1) ? gmx[i] : bound;
-              if (valid && thr == kNegInf && bound > kNegInf) {
-                publish_threshold(p, qrow, bound);
-                thr = pred_float(bound);                                 // admit scores equal to the bound
-              }
-              tightened = true;
-            } else {
-              const float before = thr;
-              tightened = joint_bound(tile_addr, ncols, s_addr, c_addr, p.kprime, target_hi, valid, cnt, thr);
-              if (valid && thr != before) publish_threshold(p, qrow, thr);
             }
-            joint_next = tightened && p.joint_after > 0;
+            thread_sort_desc<32>(gmx);
+            float kth = gmx[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) kth = (i == p.kprime - 1) ? gmx[i] : kth;
+            if (valid && thr == kNegInf && kth > kNegInf) {
+              publish_threshold(p, qrow, kth);
+              thr = ordered_to_float(float_to_ordered(kth) - 1u);     // admit scores equal to the bound
+            }
           }
         }
         if constexpr (kDense) {
 #pragma unroll 1
           for (int c = 0; c < kTileN / 32; ++c) {
             uint32_t raw[32];
-            tmem_ld_32x32b_x32(tile_addr + c * 32, raw);
+            tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
             tmem_ld_wait();
             const int64_t col0 = col_tile + c * 32;
             if (valid) {
@@ -721,45 +510,32 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
         } else {
-          // ---- pass 1 (filter): branch-free sweep over the tile with the TMEM loads software pipelined: which 32-column
-          // chunks hold a score above some row's threshold?  (Columns beyond N are TMA zero fill; a false hit on them is
-          // sorted out by the edge mask of pass 2.)
+          // ---- pass 1 (filter): branch-free sweep over the 8 chunks of 32 columns with the TMEM loads software
+          // pipelined: which chunks hold a score above some row's threshold?  (Columns beyond N are TMA zero fill;
+          // a false hit on them is sorted out by the edge mask of pass 2.)
           uint32_t hit = 0u;
           {
-#if MMD_FILTER_W == 64
-            // 64 columns per tcgen05.ld, one load in flight while the previous 64 columns are reduced: half as many
-            // load round trips per tile as with 32-column loads
-            uint32_t ra[64], rb[64];
-            tmem_ld_32x32b_x64(tile_addr, ra);
-#pragma unroll
-            for (int c = 0; c < kTileN / 64; c += 2) {
-              tmem_ld_wait();
-              tmem_ld_32x32b_x64(tile_addr + (c + 1) * 64, rb);
-              hit |= __any_sync(kFullMask, chunk_max(ra) > thr) ? (1u << (2 * c)) : 0u;
-              hit |= __any_sync(kFullMask, chunk_max(ra + 32) > thr) ? (2u << (2 * c)) : 0u;
-              tmem_ld_wait();
-              if (c + 2 < kTileN / 64) tmem_ld_32x32b_x64(tile_addr + (c + 2) * 64, ra);
-              hit |= __any_sync(kFullMask, chunk_max(rb) > thr) ? (4u << (2 * c)) : 0u;
-              hit |= __any_sync(kFullMask, chunk_max(rb + 32) > thr) ? (8u << (2 * c)) : 0u;
-            }
-#else
             uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(tile_addr, ra);
+            const uint32_t t0addr = tmem_base + lane_base + buf * kTileN;
+            tmem_ld_32x32b_x32(t0addr, ra);
 #pragma unroll
             for (int c = 0; c < kTileN / 32; c += 2) {
               tmem_ld_wait();
-              tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, rb);
+              tmem_ld_32x32b_x32(t0addr + (c + 1) * 32, rb);
               hit |= __any_sync(kFullMask, chunk_max(ra) > thr) ? (1u << c) : 0u;
               tmem_ld_wait();
-              if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(tile_addr + (c + 2) * 32, ra);
+              if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(t0addr + (c + 2) * 32, ra);
               hit |= __any_sync(kFullMask, chunk_max(rb) > thr) ? (2u << c) : 0u;
             }
-#endif
           }
-          // ---- pass 2 (collect): only the chunks that were hit are read again (next hit chunk in flight while the current
-          // one is appended from)
-          int compactions = 0;
-          auto collect_chunk = [&](int c, const uint32_t (&raw)[32]) {
+          // ---- pass 2 (collect): only the chunks that were hit are read again and appended from
+#pragma unroll 1
+          while (hit) {
+            const int c = __ffs(hit) - 1;
+            hit &= hit - 1;
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+            tmem_ld_wait();
             const int64_t col0 = col_tile + c * 32;
             float v[32];
 #pragma unroll
@@ -779,59 +555,25 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
-              if (__any_sync(kFullMask, cnt > p.trig_level)) {
-                // some row is (nearly) full: every row of the warp that holds more than K' entries sheds its tail
+              const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
+              if (need) {
                 const float before = thr;
-                const uint32_t failed = compact_local(s_addr, c_addr, p.kprime, target_hi, cnt, thr);
-                if (failed) {
-                  const RowState st = compact_rows<CAP, false>(wbase, failed, lane, p.kprime, cnt, thr, nullptr, 0);
-                  cnt = st.cnt;
-                  thr = st.thr;
-                }
+                const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
+                cnt = st.cnt;
+                thr = st.thr;
                 if (thr != before) publish_threshold(p, qrow, thr);
-                ++compactions;
               }
-              // branch-free appends: score bits and ~column stored under a predicate
+              // branch-free appends: raw entry {~column, score bits} stored under a predicate
               const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float x = v[g * 8 + j];
                 const bool take = x > thr;
-                const uint32_t off = static_cast<uint32_t>(cnt) * kSlotStride;
-                st_shared_b32_pred(s_addr + off, __float_as_uint(x), take);
-                st_shared_b32_pred(c_addr + off, ncol - j, take);
+                st_shared_v2_pred(row_addr + static_cast<uint32_t>(cnt) * 256u, ncol - j, __float_as_uint(x), take);
                 cnt += take ? 1 : 0;
               }
             }
-          };
-          if (hit) {
-            uint32_t ra[32], rb[32];
-            int ca = __ffs(hit) - 1, cb = -1;
-            hit &= hit - 1;
-            tmem_ld_32x32b_x32(tile_addr + ca * 32, ra);
-#pragma unroll 1
-            while (true) {
-              tmem_ld_wait();
-              cb = -1;
-              if (hit) {
-                cb = __ffs(hit) - 1;
-                hit &= hit - 1;
-                tmem_ld_32x32b_x32(tile_addr + cb * 32, rb);
-              }
-              collect_chunk(ca, ra);
-              if (cb < 0) break;
-              tmem_ld_wait();
-              ca = -1;
-              if (hit) {
-                ca = __ffs(hit) - 1;
-                hit &= hit - 1;
-                tmem_ld_32x32b_x32(tile_addr + ca * 32, ra);
-              }
-              collect_chunk(cb, rb);
-              if (ca < 0) break;
-            }
           }
-          if (p.joint_after > 0 && compactions >= p.joint_after) joint_next = true;
         }
         // every score of the tile has been looked at: hand the TMEM buffer back to the MMA issuer
         tc_fence_before();
@@ -847,7 +589,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int64_t row0 = cta_row0 + quarter * 32;
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
         const float before = thr;
-        const RowState st = compact_rows<CAP, true>(wbase, vmask, lane, p.kprime, cnt, thr, out_rows,
+        const RowState st = compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
                                                     static_cast<int64_t>(p.n_strips) * p.kprime);
         cnt = st.cnt;
         thr = st.thr;
@@ -1230,17 +972,6 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   p.n_m = sch.n_m; p.n_n = sch.n_n; p.tiles_per_strip = sch.T; p.n_strips = sch.S; p.n_units = sch.n_units;
   p.kprime = k;
   p.a_rows = a_rows; p.key_warps = key_warps;
-  {
-    // tuning knobs of the candidate-buffer maintenance (env overrides for sweeps; defaults from measurements)
-    static const int win = [] { const char* e = getenv("MMD_WINDOW"); return e ? atoi(e) : 4; }();
-    static const int trig = [] { const char* e = getenv("MMD_TRIGGER"); return e ? atoi(e) : 0; }();      // 0 = when < 8 slots are free
-    static const int joint = [] { const char* e = getenv("MMD_JOINT_AFTER"); return e ? atoi(e) : 2; }();
-    p.target_hi = compaction_target(cap, k, win < 0 ? 0 : win);
-    p.trig_level = cap - 8;
-    if (trig > 0 && k + trig < p.trig_level) p.trig_level = k + trig;
-    if (p.trig_level < p.target_hi) p.trig_level = p.target_hi;          // (a compaction must be able to get below the trigger)
-    p.joint_after = joint;
-  }
   p.stages = stages_for(cap, cta, a_rows, key_warps);
   p.partial = static_cast<uint64_t*>(workspace);
   if (thr_local == nullptr) {
