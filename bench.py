@@ -66,11 +66,12 @@ def parse_args():
                     help="replay the step from CUDA graphs.  auto: only for the sub-millisecond single-GPU workloads (c1, c2), where "
                          "eager launches are host-bound (c2: 1.9 ms/step eager vs 0.73 ms replayed); measured equal to eager "
                          "launches on c3 at 1, 2 and 8 GPUs, where eager launches keep one fused-kernel timing per step")
-    ap.add_argument("--rescore", default="global", choices=["global", "local"],
-                    help="N>1: exact re-score after the global candidate merge (default) or per shard before the exchange")
+    ap.add_argument("--rescore", default="auto", choices=["auto", "global", "local"],
+                    help="N>1: exact re-score after the global candidate merge (bf16 default) or per shard before the exchange "
+                         "(fp8 default: lossy candidates, every shard's K' list is kept)")
     ap.add_argument("--phases", type=int, default=0,
-                    help="1 GPU: launches per sweep of the corpus, the merged K-th best carried between them as pruning bound "
-                         "(0 = 4 for c5, 1 otherwise)")
+                    help="1 GPU: launches per sweep of the corpus (or of every split), the merged K-th best carried between them as "
+                         "pruning bound (0 = 1)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how the per-rank top-K lists are exchanged (peer-memory stores from the re-score kernel, or NCCL all-gather)")
     return ap.parse_args()
@@ -368,7 +369,7 @@ def measure_fp8_peak(torch, device):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, want_e2e=True, exchange="auto", graph="auto",
-                     rescore="global", phases=0, want_stream=True):
+                     rescore=None, phases=0, want_stream=True):
     from mmd_retrieval.sharded import ShardedCorpus, shard_bounds
     q_n, c_n, dim, k, op, kind, eps = WORKLOADS[name]
     parts = max(world, BUILT_FOR.get(name, 1))
@@ -408,7 +409,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
         t1.record()
     torch.cuda.synchronize()
     prep_ms = t0.elapsed_time(t1)
-    sc.phases = phases if phases > 0 else (4 if name == "c5" else 1)
+    sc.phases = phases if phases > 0 else 1
 
     def barrier():
         if world > 1:
@@ -565,7 +566,7 @@ def measure_workload(m, dist, torch, name, world, rank, device, steps, warmup, w
             "exchange": sc.exchange if world > 1 else "none (1 GPU)", "launch_mode": graph_note, "phases": sc.phases if world == 1 else 1,
             "stage_order": (("three flag-synchronised stages per rank (candidates -> merge + re-score of owned candidates -> finish), "
                              f"{len(sc._sub_sizes(q_n))} pipelined sub-batches per call") if sc.exchange == "peer" else
-                            ("rescore after the global candidate merge" if rescore == "global" else "rescore per shard, one exchange"))
+                            ("rescore after the global candidate merge" if sc.rescore == "global" else "rescore per shard, one exchange"))
             if world > 1 else "single shard"}
 
 
@@ -624,7 +625,7 @@ def run_ours(args):
     if WORKLOADS[args.workload][4] == "fp8":
         fp8_peak = measure_fp8_peak(torch, device)                 # before the corpus fills the HBM; every rank (keeps them in step)
     res = measure_workload(m, dist, torch, args.workload, world, rank, device, args.steps, args.warmup, exchange=args.exchange,
-                           graph=args.graph, rescore=args.rescore, phases=args.phases, want_stream=not args.no_extra)
+                           graph=args.graph, rescore=None if args.rescore == "auto" else args.rescore, phases=args.phases, want_stream=not args.no_extra)
     extra = {}
     if world == 1 and not args.no_extra:
         k1 = k1_line(torch, m, res["sc"], peaks, device)

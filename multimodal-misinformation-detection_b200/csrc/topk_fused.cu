@@ -25,6 +25,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -53,6 +54,7 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
 constexpr int kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
+constexpr int kMaxLevels = 4;        // merged bounds: quantile levels 1..4 (2 + 4 + 8 + 16 slots per query)
 
 struct FusedParams {
   int64_t Q, N;
@@ -65,8 +67,12 @@ struct FusedParams {
   int stages;
   int a_rows;            // query rows staged per CTA and K block: 128, or the 32-row groups a batch of < 128 queries fills
   int key_warps;         // epilogue warps (lane quarters 0 .. key_warps-1) that own candidate buffers: a_rows / 32
+  int keep_hi;           // long lists (CAP > 64): a compaction by selection leaves between kprime and keep_hi entries
+  int early_level;       //   ... and takes along every row of the warp that holds more than this many
+  int levels;            // merged bounds: levels 1..levels of quantile slots in lvl (0 = off)
   uint64_t* partial;     // [Q][S][kprime] keys
   uint32_t* thr_global;  // [Q] shared lower bounds of every query's K-th best (ordered uint, 0 = none yet)
+  uint32_t* lvl;         // [level_slots(levels)][Q] ordered score words, 0 = empty (see "merged bounds")
   uint32_t* thr_peer[8]; // row-sharded corpus: the same array on EVERY rank (peer-mapped, own one included); a bound
   int n_thr_peers;       //   learnt on one shard prunes all of them.  0 = publish to thr_global only.
   float* dense;          // dense mode: [Q][ldd] scores
@@ -81,8 +87,26 @@ struct FusedParams {
 //   stats[tile*8 + 0] MMA: before tmem_empty wait   [1] MMA: after wait   [2] MMA: all MMAs of the tile issued
 //   stats[tile*8 + 4] EPI(warp 2): before tmem_full wait   [5] after wait   [6] tile processed
 #define MMD_TRACE(tile, slot) do { if (p.stats && blockIdx.x == 0 && (tile) < 128) p.stats[(tile) * 8 + (slot)] = clock64(); } while (0)
+// ... and whole-launch aggregates (summed over CTAs / epilogue warps) in stats[1024 + slot]:
+//   MMA issuer:  0 cycles waiting for a free accumulator (epilogue-bound)   1 waiting for operands (load-bound)   2 busy in total
+//   epilogue:    8 waiting for an accumulator   9 cold start   10 filter pass   11 collect pass without compactions
+//                12 compactions   13 end of unit (final sort, publication)   14 busy in total
+//                16 tiles   17 hit chunks   18 group visits   19 compaction calls   20 rows compacted   21 appends   22 units
+enum { kStMmaEmpty = 0, kStMmaFull = 1, kStMmaTotal = 2, kStEpiWait = 8, kStEpiCold = 9, kStEpiFilter = 10, kStEpiCollect = 11,
+       kStEpiCompact = 12, kStEpiFinal = 13, kStEpiTotal = 14, kStTiles = 16, kStHitChunks = 17, kStGroups = 18, kStCompCalls = 19,
+       kStCompRows = 20, kStAppends = 21, kStUnits = 22, kStSlots = 24 };
+#define MMD_ST_DECL long long st_acc[kStSlots] = {0}; long long st_t = 0; (void)st_t
+#define MMD_ST_T0() do { st_t = clock64(); } while (0)
+#define MMD_ST_ACC(slot) do { const long long now_ = clock64(); st_acc[slot] += now_ - st_t; st_t = now_; } while (0)
+#define MMD_ST_ADD(slot, v) do { st_acc[slot] += (v); } while (0)
+#define MMD_ST_FLUSH() do { if (p.stats && lane == 0) for (int i_ = 0; i_ < kStSlots; ++i_) if (st_acc[i_]) atomicAdd(p.stats + 1024 + i_, (unsigned long long)st_acc[i_]); } while (0)
 #else
 #define MMD_TRACE(tile, slot) do { } while (0)
+#define MMD_ST_DECL do { } while (0)
+#define MMD_ST_T0() do { } while (0)
+#define MMD_ST_ACC(slot) do { } while (0)
+#define MMD_ST_ADD(slot, v) do { } while (0)
+#define MMD_ST_FLUSH() do { } while (0)
 #endif
 
 struct SmemLayout {
@@ -171,6 +195,17 @@ struct RowState {
   float thr;
 };
 
+// Quantile bounds a finished unit leaves behind (see "merged bounds" above the kernel): where to publish them.
+struct LevelPub {
+  uint32_t* lvl;      // nullptr: nothing to publish
+  int64_t Q;
+  int64_t row0;       // query row of this warp's row 0
+  int strip;
+  int levels;
+};
+__host__ __device__ constexpr int level_slot0(int j) { return (1 << j) - 2; }        // first slot of level j >= 1
+__host__ __device__ constexpr int level_slots(int levels) { return (2 << levels) - 2; }
+
 // Sort the candidate buffers of the rows named in `mask` (R of them at a time); keep the best `kprime`.
 //   FINAL = false : write the survivors back.
 //   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
@@ -178,7 +213,7 @@ struct RowState {
 // holds kprime, its threshold is at least its kprime-th best score.
 template <int CAP, bool FINAL, int R, int E>
 __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int& cnt,
-                                              float& thr, uint64_t* out_rows, int64_t out_row_stride) {
+                                              float& thr, uint64_t* out_rows, int64_t out_row_stride, const LevelPub& pub) {
   // E = registers per lane and row (CAP / 32)
   uint64_t k[R][E];
   int n[R];
@@ -209,6 +244,19 @@ __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)
         const int i = e * 32 + lane;
         if (i < kprime) out[i] = k[r][e];   // empty slots are key 0
       }
+      if (pub.lvl != nullptr) {
+        // the score at rank ceil(K' / 2^j) of this strip's list, for every level j: see merged bounds
+        for (int j = 1; j <= pub.levels; ++j) {
+          const int rank = (kprime + (1 << j) - 1) >> j;
+          const int idx = rank - 1;
+          uint64_t kq = k[r][0];
+#pragma unroll
+          for (int e = 1; e < E; ++e) kq = ((idx >> 5) == e) ? k[r][e] : kq;
+          if (lane == (idx & 31) && n[r] >= rank)
+            atomicMax(pub.lvl + static_cast<int64_t>(level_slot0(j) + (pub.strip & ((1 << j) - 1))) * pub.Q + pub.row0 + rows[r],
+                      static_cast<uint32_t>(kq >> 32));
+        }
+      }
     }
     uint64_t kk = k[r][0];
 #pragma unroll
@@ -221,26 +269,150 @@ __device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)
   }
 }
 
+// Selection instead of a sort (long lists, where a compaction frees few slots and must be cheap): the row's entries are
+// spread over the lanes (E per lane); bisection on the order-preserving score word, counting "entries above the midpoint"
+// with one warp reduction per step, finds a bound with between kprime and keep_hi entries above it; those are written back
+// densely (ballot prefix), the bound becomes the row's threshold.  The buffer stays unsorted -- only the end of a unit
+// needs the order.  ~10 steps of E compares + 1 reduction for R rows at once instead of a 32*E-wide bitonic network.
+// Returns the mask of rows that did not converge (more equal scores around the kprime-th best than the window holds):
+// the caller sorts those.
+template <int CAP, int R>
+__device__ __forceinline__ uint32_t select_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int keep_hi,
+                                                 int& cnt, float& thr) {
+  constexpr int E = CAP / 32;
+  uint32_t ord[R][E], col[R][E];
+  uint32_t lo[R], hi[R];
+  int c_lo[R];
+  bool done[R], ok[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int n = __shfl_sync(kFullMask, cnt, rows[r]);
+    uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      const uint64_t raw = (i < n) ? wkeys[key_slot_index(i, rows[r])] : 0ull;
+      const uint32_t o = (i < n) ? float_to_ordered(__uint_as_float(static_cast<uint32_t>(raw >> 32))) : 0u;
+      ord[r][e] = o;                                   // real scores map to >= 0x007fffff; 0 = empty slot
+      col[r][e] = static_cast<uint32_t>(raw);
+      mn = (i < n) ? min(mn, o) : mn;
+      mx = max(mx, o);
+    }
+    // invariant: count(> lo) = c_lo >= kprime (the row holds at least kprime entries when it is compacted), count(> hi) < kprime
+    lo[r] = __reduce_min_sync(kFullMask, mn) - 1u;
+    hi[r] = __reduce_max_sync(kFullMask, mx);
+    c_lo[r] = n;
+    ok[r] = n <= keep_hi || n < kprime;
+    done[r] = ok[r];
+  }
+  // three probes per step (the interval shrinks to a quarter; the three warp reductions are independent, and a step is a
+  // chain of dependent instructions with nothing else to issue in between)
+#pragma unroll 1
+  for (int it = 0; it < 40; ++it) {
+    bool all_done = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) all_done = all_done && done[r];
+    if (all_done) break;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t d = hi[r] - lo[r];
+      const uint32_t q = d >> 2;
+      // d < 4: one midpoint (three equal probes); d = 1: the midpoint is lo itself -> equal scores straddle the kprime-th best
+      const uint32_t t1 = q ? lo[r] + q : lo[r] + (d >> 1), t2 = q ? t1 + q : t1, t3 = q ? t2 + q : t1;
+      int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c1 += (ord[r][e] > t1) ? 1 : 0;
+        c2 += (ord[r][e] > t2) ? 1 : 0;
+        c3 += (ord[r][e] > t3) ? 1 : 0;
+      }
+      c1 = __reduce_add_sync(kFullMask, c1);
+      c2 = __reduce_add_sync(kFullMask, c2);
+      c3 = __reduce_add_sync(kFullMask, c3);
+      if (!done[r]) {
+        if (t1 == lo[r]) {
+          done[r] = true;
+        } else {
+          if (c3 >= kprime) { lo[r] = t3; c_lo[r] = c3; }
+          else if (c2 >= kprime) { lo[r] = t2; c_lo[r] = c2; hi[r] = t3; }
+          else if (c1 >= kprime) { lo[r] = t1; c_lo[r] = c1; hi[r] = t2; }
+          else { hi[r] = t1; }
+          done[r] = ok[r] = c_lo[r] <= keep_hi;
+        }
+      }
+    }
+  }
+  uint32_t failed = 0u;
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!ok[r]) {
+      failed |= 1u << rows[r];
+      continue;
+    }
+    if (c_lo[r] < kprime || lo[r] + 1u == 0u) continue;      // (short row: left alone)
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool keep = ord[r][e] > lo[r];
+      const uint32_t b = __ballot_sync(kFullMask, keep);
+      const int pos = base + __popc(b & lt);
+      if (keep)
+        wkeys[key_slot_index(pos, rows[r])] =
+            (static_cast<uint64_t>(__float_as_uint(ordered_to_float(ord[r][e]))) << 32) | col[r][e];
+      base += __popc(b);
+    }
+    if (lane == rows[r]) {
+      cnt = base;
+      thr = fmaxf(thr, ordered_to_float(lo[r]));   // kprime entries of the row lie strictly above it
+    }
+  }
+  return failed;
+}
+
+// keep_hi: see select_batch (long lists only; short lists are sorted, which also gives them the exact kprime-th best as bound).
 template <int CAP, bool FINAL>
-__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int cnt, float thr,
-                                              uint64_t* out_rows, int64_t out_row_stride) {
+__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int keep_hi, int cnt, float thr,
+                                              uint64_t* out_rows, int64_t out_row_stride, LevelPub pub) {
   constexpr int R = CAP == 64 ? 4 : 2;
   constexpr int E = CAP / 32;
   __syncwarp();
-  while (__popc(mask) >= R) {
-    int rows[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      rows[r] = __ffs(mask) - 1;
+  if constexpr (!FINAL && CAP > 64) {
+    // (one row at a time in a loop: the rarely executed paths of this kernel run out of a cold instruction cache, and one
+    //  row's worth of code that the following rows reuse beat the four-rows-interleaved variant by a wide margin)
+    uint32_t failed = 0u;
+#pragma unroll 1
+    while (mask) {
+      int rows[1];
+      rows[0] = __ffs(mask) - 1;
       mask &= mask - 1;
+      failed |= select_batch<CAP, 1>(wkeys, rows, lane, kprime, keep_hi, cnt, thr);
     }
-    compact_batch<CAP, FINAL, R, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+    mask = failed;
+    __syncwarp();
   }
-  while (mask) {
-    int rows[1];
-    rows[0] = __ffs(mask) - 1;
-    mask &= mask - 1;
-    compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride);
+  // One instantiation of the network per use (the kernel's rarely executed code runs out of a cold instruction cache:
+  // fewer, reused instructions beat more parallel ones).  End of unit: R rows interleaved, all rows of the warp at once
+  // (a short last batch repeats its last row: same results written twice).  In between: the row that is full, alone.
+  if constexpr (FINAL) {
+#pragma unroll 1
+    while (mask) {
+      int rows[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        rows[r] = mask ? __ffs(mask) - 1 : rows[r > 0 ? r - 1 : 0];
+        mask &= mask - 1;
+      }
+      compact_batch<CAP, FINAL, R, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
+    }
+  } else {
+#pragma unroll 1
+    while (mask) {
+      int rows[1];
+      rows[0] = __ffs(mask) - 1;
+      mask &= mask - 1;
+      compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
+    }
   }
   __syncwarp();
   RowState st;
@@ -281,13 +453,25 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 
+// Bit g set <=> one of columns 4g .. 4g+3 of the 32 loaded scores lies above the row's threshold (NaN never does).
+__device__ __forceinline__ uint32_t group_mask(const uint32_t (&r)[32], float thr) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float mx = fmaxf(fmaxf(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])),
+                           fmaxf(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+    m |= (mx > thr) ? (1u << g) : 0u;
+  }
+  return m;
+}
+
 // Thresholds are shared between CTAs through thr_global[q] (order-preserving uint, atomicMax).  A published
 // value is the next float BELOW a row's current K-th best, so that "score > bound" still admits a score equal
 // to that K-th best (the (score desc, row asc) tie rule is decided later, by the sorts).  Any K-th best of a
 // subset of the corpus is a valid lower bound for the K-th best of the whole corpus.
 // With a row-sharded corpus the K-th best of one GPU's shard is equally a lower bound for the global K-th best, so a
 // publication goes to the threshold array of every rank (system-scope atomics over NVLink on peer-mapped memory).
-__device__ __forceinline__ void publish_threshold(const FusedParams& p, int64_t qrow, float thr) {
+__device__ __noinline__ void publish_threshold(const FusedParams& p, int64_t qrow, float thr) {
   const uint32_t v = float_to_ordered(thr) - 1u;
   if (p.n_thr_peers == 0) {
     atomicMax(p.thr_global + qrow, v);
@@ -296,6 +480,15 @@ __device__ __forceinline__ void publish_threshold(const FusedParams& p, int64_t 
   }
 }
 
+// Merged bounds.  thr_global[q] carries the best K'-th best any ONE unit (strip) has seen; the K'-th best of the UNION of
+// the strips processed so far is much higher (with s finished strips of n rows each roughly the (K'/s)-th best of one
+// strip), and the fraction of scores that pass the filter -- hence collect passes and compactions -- falls with it.  A full
+// merge of finished lists inside the sweep would be expensive; quantiles are enough: a finished unit publishes, for
+// levels j = 1..J, its score at rank r_j = ceil(K' / 2^j) into slot (strip mod 2^j) of level j (atomicMax).  The slots of a
+// level belong to disjoint sets of strips, each slot's value has r_j scores of ONE strip at or above it, so the minimum
+// over the 2^j slots of a level has 2^j * r_j >= K' distinct corpus rows at or above it: a valid lower bound of the
+// query's K'-th best.  Every finishing unit folds the levels (max over levels of the min over slots) into thr_global,
+// where the running units pick it up with their per-tile read.
 // ---------------------------------------------------------------- the kernel
 // kCta = 1: one CTA per SM, UMMA 128 x 256.
 // kCta = 2: clusters of two CTAs (one TPC); the pair runs ONE tcgen05.mma.cta_group::2 of 256 queries x 256
@@ -389,6 +582,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
+      MMD_ST_DECL;
+#ifdef MMD_STATS
+      const long long st_begin = clock64();
+#endif
       for (int u = unit0; u < p.n_units; u += unit_stride) {
         const int strip = u / p.n_m;
         const int t0 = strip * T;
@@ -396,12 +593,16 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int t = t0; t < t1; ++t, ++it) {
           const uint32_t buf = it & 1;
           MMD_TRACE(it, 0);
+          MMD_ST_T0();
           mbar_wait<kCta == 2>(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, p.status, 2);
+          MMD_ST_ACC(kStMmaEmpty);
           MMD_TRACE(it, 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kTileN;
           for (int kb = 0; kb < p.kblocks; ++kb) {
+            MMD_ST_T0();
             mbar_wait(&full_bar[stage], phase, p.status, 3);
+            MMD_ST_ACC(kStMmaFull);
             tc_fence_after();
             // (with a_rows = 32 the 128-row A descriptor also covers what follows the staged rows: those accumulator
             //  lanes belong to query rows >= Q, which no epilogue thread ever reads a candidate from)
@@ -422,6 +623,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           MMD_TRACE(it, 2);
         }
       }
+#ifdef MMD_STATS
+      st_acc[kStMmaTotal] = clock64() - st_begin;
+#endif
+      MMD_ST_FLUSH();
     }
   } else {
     // ===================================================== epilogue warps (2..5)
@@ -435,6 +640,11 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const float kNegInf = __int_as_float(0xff800000);
     const float kPosInf = __int_as_float(0x7f800000);
     uint32_t it = 0;
+    MMD_ST_DECL;
+#ifdef MMD_STATS
+    const long long st_begin = clock64();
+    long long st_appends = 0;
+#endif
     for (int u = unit0; u < p.n_units; u += unit_stride) {
       const int m_tile = u % p.n_m;
       const int strip = u / p.n_m;
@@ -445,7 +655,10 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const bool valid = qrow < p.Q;
       float thr = valid ? kNegInf : kPosInf;
       int cnt = 0;
+      MMD_ST_ADD(kStUnits, 1);
       for (int t = t0; t < t1; ++t, ++it) {
+        MMD_ST_ADD(kStTiles, 1);
+        MMD_ST_T0();
         const uint32_t buf = it & 1;
         // pick up what other CTAs (and earlier strips) have learnt about this row while the MMAs finish
         uint32_t shared_bound = 0u;
@@ -455,6 +668,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (warp == 2 && lane == 0) MMD_TRACE(it, 4);
         mbar_wait(&tmem_full[buf], (it >> 1) & 1, p.status, 4);
         if (warp == 2 && lane == 0) MMD_TRACE(it, 5);
+        MMD_ST_ACC(kStEpiWait);
         tc_fence_after();
         if constexpr (!kDense) {
           if (shared_bound != 0u) thr = fmaxf(thr, ordered_to_float(shared_bound));
@@ -495,6 +709,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
         }
+        MMD_ST_ACC(kStEpiCold);
         if constexpr (kDense) {
 #pragma unroll 1
           for (int c = 0; c < kTileN / 32; ++c) {
@@ -510,70 +725,85 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
           }
         } else {
-          // ---- pass 1 (filter): branch-free sweep over the 8 chunks of 32 columns with the TMEM loads software
-          // pipelined: which chunks hold a score above some row's threshold?  (Columns beyond N are TMA zero fill;
-          // a false hit on them is sorted out by the edge mask of pass 2.)
-          uint32_t hit = 0u;
+          // ---- pass 1 (filter): branch-free sweep over the tile, 32 columns per tcgen05.ld, two loads in flight: the maxima
+          // of the tile's 64 groups of 4 columns against the row threshold -> a 64-bit mask per thread, OR-ed over the warp:
+          // the groups that hold a candidate for SOME row.  The sweep runs at the TMEM read rate (~65 cycles per load); the
+          // mask arithmetic hides under it.  (Columns beyond N are TMA zero fill; a false hit on them is sorted out in pass 2.)
+          const uint32_t tile_addr = tmem_base + lane_base + buf * kTileN;
+          uint32_t w0 = 0u, w1 = 0u;
           {
             uint32_t ra[32], rb[32];
-            const uint32_t t0addr = tmem_base + lane_base + buf * kTileN;
-            tmem_ld_32x32b_x32(t0addr, ra);
+            tmem_ld_32x32b_x32(tile_addr, ra);
 #pragma unroll
             for (int c = 0; c < kTileN / 32; c += 2) {
               tmem_ld_wait();
-              tmem_ld_32x32b_x32(t0addr + (c + 1) * 32, rb);
-              hit |= __any_sync(kFullMask, chunk_max(ra) > thr) ? (1u << c) : 0u;
+              tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, rb);
+              const uint32_t ma = group_mask(ra, thr) << ((c & 3) * 8);
               tmem_ld_wait();
-              if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(t0addr + (c + 2) * 32, ra);
-              hit |= __any_sync(kFullMask, chunk_max(rb) > thr) ? (2u << c) : 0u;
+              if (c + 2 < kTileN / 32) tmem_ld_32x32b_x32(tile_addr + (c + 2) * 32, ra);
+              const uint32_t mb = group_mask(rb, thr) << (((c + 1) & 3) * 8);
+              if (c < 4) w0 |= ma | mb; else w1 |= ma | mb;
             }
           }
-          // ---- pass 2 (collect): only the chunks that were hit are read again and appended from
+          uint64_t wanted = (static_cast<uint64_t>(__reduce_or_sync(kFullMask, w1)) << 32) | __reduce_or_sync(kFullMask, w0);
+          MMD_ST_ACC(kStEpiFilter);
+          MMD_ST_ADD(kStHitChunks, wanted != 0ull ? 1 : 0);
+          // ---- pass 2 (collect): only the wanted groups are appended from.  (Round 1 re-read whole 32-column chunks and
+          // voted per 8-column group: ~900 cycles per marked chunk, two thirds of the epilogue's busy time in every shape.)
+          const uint32_t col_lo = static_cast<uint32_t>(col_tile);                                  // (N < 2^31)
+          const int cols_here = edge ? static_cast<int>(p.N - col_tile) : kTileN;
+          auto visit = [&](int grp, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+            MMD_ST_ADD(kStGroups, 1);
+            uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 4);
+            if (need) {
+              // (long lists: rows that are nearly full come along, several rows share one pass of the selection)
+              if constexpr (CAP > 64) need = __ballot_sync(kFullMask, cnt > p.early_level);
+              MMD_ST_ACC(kStEpiCollect);
+              MMD_ST_ADD(kStCompCalls, 1);
+              MMD_ST_ADD(kStCompRows, __popc(need));
+              const float before = thr;
+              const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, p.keep_hi, cnt, thr, nullptr, 0, LevelPub{});
+              cnt = st.cnt;
+              thr = st.thr;
+              if (thr != before) publish_threshold(p, qrow, thr);
+              MMD_ST_ACC(kStEpiCompact);
+            }
+            // branch-free appends: raw entry {~column, score bits} stored under a predicate
+            const uint32_t ncol = ~(col_lo + static_cast<uint32_t>(grp * 4));
+            const int left = cols_here - grp * 4;              // columns of this group that exist (>= 4 except at the corpus end)
+            const uint32_t xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool take = __uint_as_float(xs[j]) > thr && j < left;
+              st_shared_v2_pred(row_addr + static_cast<uint32_t>(cnt) * 256u, ncol - j, xs[j], take);
+              cnt += take ? 1 : 0;
+#ifdef MMD_STATS
+              st_appends += take ? 1 : 0;
+#endif
+            }
+          };
+          // 4 columns per tcgen05.ld, up to four loads in flight
 #pragma unroll 1
-          while (hit) {
-            const int c = __ffs(hit) - 1;
-            hit &= hit - 1;
-            uint32_t raw[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_base + buf * kTileN + c * 32, raw);
+          while (wanted != 0ull) {
+            uint32_t v[4][4];
+            int grp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              grp[i] = -1;
+              if (wanted != 0ull) {
+                grp[i] = __ffsll(static_cast<long long>(wanted)) - 1;
+                wanted &= wanted - 1ull;
+                tmem_ld_32x32b_x4(tile_addr + grp[i] * 4, v[i]);
+              }
+            }
             tmem_ld_wait();
-            const int64_t col0 = col_tile + c * 32;
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-            if (edge) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j >= p.N) v[j] = kNegInf;
-            }
-            float gm[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
-              const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-              gm[g] = fmaxf(a, b);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (!__any_sync(kFullMask, gm[g] > thr)) continue;      // nobody in the warp wants these 8 columns
-              const uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 8);
-              if (need) {
-                const float before = thr;
-                const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, cnt, thr, nullptr, 0);
-                cnt = st.cnt;
-                thr = st.thr;
-                if (thr != before) publish_threshold(p, qrow, thr);
-              }
-              // branch-free appends: raw entry {~column, score bits} stored under a predicate
-              const uint32_t ncol = ~static_cast<uint32_t>(col0 + g * 8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float x = v[g * 8 + j];
-                const bool take = x > thr;
-                st_shared_v2_pred(row_addr + static_cast<uint32_t>(cnt) * 256u, ncol - j, __float_as_uint(x), take);
-                cnt += take ? 1 : 0;
-              }
+            for (int i = 0; i < 4; ++i) {
+              if (grp[i] < 0) break;
+              visit(grp[i], v[i][0], v[i][1], v[i][2], v[i][3]);
             }
           }
+          MMD_ST_ACC(kStEpiCollect);
         }
         // every score of the tile has been looked at: hand the TMEM buffer back to the MMA issuer
         tc_fence_before();
@@ -585,17 +815,35 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       if constexpr (!kDense) {
         // unit done: emit the sorted K-list of every valid row of this warp
+        MMD_ST_T0();
         const uint32_t vmask = __ballot_sync(kFullMask, valid);
         const int64_t row0 = cta_row0 + quarter * 32;
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
         const float before = thr;
-        const RowState st = compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, cnt, thr, out_rows,
-                                                    static_cast<int64_t>(p.n_strips) * p.kprime);
+        const LevelPub pub{p.lvl, p.Q, row0, strip, p.levels};
+        const RowState st = compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, p.keep_hi, cnt, thr, out_rows,
+                                                    static_cast<int64_t>(p.n_strips) * p.kprime, pub);
         cnt = st.cnt;
         thr = st.thr;
         if (valid && thr != before) publish_threshold(p, qrow, thr);
+        if (p.lvl != nullptr && valid) {
+          // merged bound: fold what the finished strips have left in the quantile slots (this unit's included)
+          uint32_t best = 0u;
+          for (int j = 1; j <= p.levels; ++j) {
+            uint32_t m = 0xffffffffu;
+            for (int s = 0; s < (1 << j); ++s) m = min(m, __ldcg(p.lvl + static_cast<int64_t>(level_slot0(j) + s) * p.Q + qrow));
+            best = max(best, m);                       // an empty slot (0) voids its level
+          }
+          if (best != 0u && ordered_to_float(best) > thr) publish_threshold(p, qrow, ordered_to_float(best));
+        }
+        MMD_ST_ACC(kStEpiFinal);
       }
     }
+#ifdef MMD_STATS
+    st_acc[kStEpiTotal] = clock64() - st_begin;
+    st_acc[kStAppends] = __reduce_add_sync(kFullMask, static_cast<int>(st_appends));
+#endif
+    MMD_ST_FLUSH();
   }
 
   tc_fence_before();
@@ -905,7 +1153,7 @@ extern "C" size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op
   PreparedLayout lay;
   if (!prepared_layout(op_dtype, dim, &lay)) return 0;
   const Schedule sch = plan_schedule(Q, N, k, sm_count(), static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)), cta_mode_for(Q));
-  return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + static_cast<size_t>(Q) * sizeof(uint32_t) + 256;
+  return static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t) + static_cast<size_t>(Q) * sizeof(uint32_t) * (1 + level_slots(kMaxLevels)) + 256;
 }
 
 namespace mmd {
@@ -951,7 +1199,7 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   const int cta = cta_mode_for(Q);
   const Schedule sch = plan_schedule(Q, N, k, sms, static_cast<int>(ceil_div(lay.row_bytes, kBlockKBytes)), cta);
   const size_t keys_bytes = static_cast<size_t>(Q) * sch.S * k * sizeof(uint64_t);
-  const size_t need = keys_bytes + static_cast<size_t>(Q) * sizeof(uint32_t);
+  const size_t need = keys_bytes + static_cast<size_t>(Q) * sizeof(uint32_t) * (1 + level_slots(kMaxLevels));
   if (workspace == nullptr || workspace_bytes < need) {
     set_last_error("mmd_topk_scores: workspace %zu < %zu bytes", workspace_bytes, need);
     return MMD_ERR_WORKSPACE;
@@ -984,6 +1232,23 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
     p.n_thr_peers = n_thr;
     for (int i = 0; i < n_thr; ++i) p.thr_peer[i] = static_cast<uint32_t*>(thr_all_host[i]);
   }
+  {
+    // long lists: selection window and early inclusion (see select_batch); merged bounds: as many levels as strips fill
+    const int slack = cap - 4 - k;                         // appends a row can take between two compactions (4 per visit)
+    p.keep_hi = k + (slack / 8 > 1 ? slack / 8 : 1);
+    if (p.keep_hi > cap - 4) p.keep_hi = cap - 4;          // (no slack at all: the selection must be exact)
+    p.early_level = cap - 4 - slack / 4;
+    if (p.early_level < p.keep_hi) p.early_level = p.keep_hi;
+    static const int max_levels = [] { const char* e = getenv("MMD_LEVELS"); return e ? atoi(e) : kMaxLevels; }();   // tuning knob (0 = off)
+    int levels = 0;
+    while (levels < kMaxLevels && levels < max_levels && (2 << levels) <= sch.S) ++levels;
+    p.levels = levels;
+    p.lvl = nullptr;
+    if (levels > 0) {
+      p.lvl = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + keys_bytes) + Q;
+      MMD_CUDA_OK(cudaMemsetAsync(p.lvl, 0, static_cast<size_t>(Q) * sizeof(uint32_t) * level_slots(levels), st));
+    }
+  }
   p.dense = nullptr; p.ldd = 0; p.out_scale = 1.0f;
   p.status = device_status_word();
   p.stats = nullptr;
@@ -991,16 +1256,35 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
   {
     static unsigned long long* dstats = nullptr;
     static int calls = 0;
-    if (dstats == nullptr) { cudaMalloc(&dstats, 1024 * sizeof(unsigned long long)); cudaMemset(dstats, 0, 1024 * 8); }
-    if (++calls == 4) {          // dump the timeline of the previous (warm) launch once
-      unsigned long long h[1024];
+    if (dstats == nullptr) { cudaMalloc(&dstats, 2048 * sizeof(unsigned long long)); cudaMemset(dstats, 0, 2048 * 8); }
+    if (++calls == 4) {          // dump the timeline and the aggregates of the previous (warm) launch once
+      static unsigned long long h[2048];
       cudaMemcpy(h, dstats, sizeof(h), cudaMemcpyDeviceToHost);
+      {
+        const unsigned long long* a = h + 1024;
+        const double n_mma = static_cast<double>(sch.grid / cta), n_epi = static_cast<double>(sch.grid) * 4.0;
+        fprintf(stderr, "[stats] grid %d cta %d  S %d T %d units %d levels %d  k' %d\n", sch.grid, cta, sch.S, sch.T, sch.n_units, p.levels, k);
+        fprintf(stderr, "[stats] MMA issuer (avg cycles per CTA): total %.0f  waiting for accumulator %.0f (%.1f%%)  waiting for operands %.0f (%.1f%%)\n",
+                a[kStMmaTotal] / n_mma, a[kStMmaEmpty] / n_mma, 100.0 * a[kStMmaEmpty] / (a[kStMmaTotal] + 1.0), a[kStMmaFull] / n_mma,
+                100.0 * a[kStMmaFull] / (a[kStMmaTotal] + 1.0));
+        fprintf(stderr, "[stats] epilogue warp (avg cycles): total %.0f  wait %.0f  cold %.0f  filter %.0f  collect %.0f  compact %.0f  unit-end %.0f\n",
+                a[kStEpiTotal] / n_epi, a[kStEpiWait] / n_epi, a[kStEpiCold] / n_epi, a[kStEpiFilter] / n_epi, a[kStEpiCollect] / n_epi,
+                a[kStEpiCompact] / n_epi, a[kStEpiFinal] / n_epi);
+        const double tiles = a[kStTiles] + 1e-9;
+        fprintf(stderr, "[stats] per warp-tile: busy %.0f cycles (filter %.0f collect %.0f compact %.0f)  hit chunks %.2f  group visits %.2f  appends %.2f  "
+                "compaction calls %.3f rows %.3f;  cycles per compaction call %.0f, per compacted row %.0f;  unit-end %.0f cycles per warp-unit\n",
+                (a[kStEpiCold] + a[kStEpiFilter] + a[kStEpiCollect] + a[kStEpiCompact]) / tiles, a[kStEpiFilter] / tiles, a[kStEpiCollect] / tiles,
+                a[kStEpiCompact] / tiles, a[kStHitChunks] / tiles, a[kStGroups] / tiles, a[kStAppends] / tiles, a[kStCompCalls] / tiles,
+                a[kStCompRows] / tiles, a[kStEpiCompact] / (a[kStCompCalls] + 1e-9), a[kStEpiCompact] / (a[kStCompRows] + 1e-9),
+                a[kStEpiFinal] / (a[kStUnits] + 1e-9));
+      }
       const unsigned long long t0 = h[0];
       for (int t = 0; t < 128 && h[t * 8 + 2] != 0; ++t)
         fprintf(stderr, "[trace] tile %3d  mma: start %8lld waited %6lld issue-done %8lld | epi: wait-start %8lld got %8lld done %8lld\n", t,
                 (long long)(h[t * 8] - t0), (long long)(h[t * 8 + 1] - h[t * 8]), (long long)(h[t * 8 + 2] - t0),
                 (long long)(h[t * 8 + 4] - t0), (long long)(h[t * 8 + 5] - t0), (long long)(h[t * 8 + 6] - t0));
     }
+    cudaMemsetAsync(dstats + 1024, 0, 1024 * sizeof(unsigned long long), st);      // aggregates are per launch
     p.stats = dstats;
   }
 #endif

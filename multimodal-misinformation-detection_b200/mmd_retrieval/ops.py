@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import math
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -291,10 +292,37 @@ def topk_candidates(queries, pc: PreparedCorpus, k: int, overfetch: Optional[int
     return q, (q_inv if pc.metric == "cos" else None), scores, idx
 
 
+# Over-fetch factor (candidates re-scored per result row, K'/k) a low-precision candidate pass needs before its exact
+# re-score returns the fp32 top-k with recall ~1: the operand noise moves a score by sigma ~ 1.8e-3 (e4m3) / 1.4e-4 (bf16)
+# on unit-norm 768-d embeddings, and the k-th best must stay inside the candidate list.  Lists are capped at 120 entries
+# (104 with re-score), so long lists reach the factor by SPLITTING the corpus instead: see auto_splits().
+_OVERFETCH_TARGET = {"fp8": 4.0, "bf16": 1.5, "fp16": 1.5}
+_MIN_SPLIT_ROWS = 131072
+
+
+def auto_splits(op: str, k: int, kprime: int, n_rows: int) -> int:
+    """Independent sub-searches (contiguous row ranges, each with its own pruning bounds, its own K' candidates and its own
+    exact re-score; the exact lists are merged) needed to bring the effective over-fetch V * K' / k up to the target of the
+    operand type.  1 for the short lists of the default path (k = 10: K' = 18); 2 for bf16 at k = 100 (K' = 104); 3 / 4 for
+    fp8 at k = 10 / 100.  A candidate pass can only lose a true top-k row whose low-precision score ranks below K' WITHIN
+    ITS SPLIT, and a split holds only ~k/V of the true top-k (4 spare candidates at k = 100)."""
+    target = _OVERFETCH_TARGET.get(op)
+    if target is None or k <= 0 or kprime <= 0:
+        return 1
+    want = int(math.ceil(target * k / kprime - 0.05))
+    return max(1, min(want, 8, n_rows // _MIN_SPLIT_ROWS))
+
+
+def _slice_corpus(pc: PreparedCorpus, lo: int, hi: int) -> PreparedCorpus:
+    return PreparedCorpus(rows=pc.rows[lo:hi], inv_norm=None if pc.inv_norm is None else pc.inv_norm[lo:hi],
+                          source=None if pc.source is None else pc.source[lo:hi], n=hi - lo, dim=pc.dim, op=pc.op,
+                          metric=pc.metric, eps=pc.eps, idx_offset=pc.idx_offset + lo)
+
+
 def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps: Optional[float] = None,
          rescore_exact: Optional[bool] = None, overfetch: Optional[int] = None,
-         index_dtype: torch.dtype = torch.int64, dense_fallback: bool = False, phases: int = 1
-         ) -> Tuple[torch.Tensor, torch.Tensor]:
+         index_dtype: torch.dtype = torch.int64, dense_fallback: bool = False, phases: int = 1,
+         splits: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k most similar corpus rows for every query.
 
     queries : [Q,D] (or [D]) tensor / ndarray / list, any device (moved to the corpus device).
@@ -305,6 +333,8 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
     tensor-core pass and recomputes their scores in fp32 from the original embeddings.
     phases > 1: the corpus is swept in that many launches with the merged K-th best carried between them as pruning bound
     (see topk_prepared_phased; for long lists over large corpora).
+    splits (with the exact re-score; default auto_splits()): independent sub-searches over contiguous row ranges, each
+    re-scored exactly, exact lists merged -- the effective over-fetch of long lists / fp8 candidates.
     dense_fallback: k beyond the fused selection's limit (120) is served by the dense tensor-core contraction plus a
     device-side stable sort of the score rows (query chunks of <= 1 GB of scores) -- off the hot path, for drop-in
     completeness only (the reference's largest list is top_k*10 = 100, experiment_text.py:26).
@@ -331,8 +361,20 @@ def topk(queries, corpus, k: int, metric: str = "cos", dtype: str = "bf16", eps:
     if do_rescore and pc.source is None:
         raise ValueError("rescore_exact=True needs a PreparedCorpus built with keep_source=True")
     if do_rescore:
-        q, q_inv, _, cand = topk_candidates(q, pc, k_eff, overfetch, phases=phases)
-        scores, idx = rescore(q, q_inv, pc, cand, k_eff)
+        kprime = overfetch_for(k_eff, pc.n) if overfetch is None else max(k_eff, min(int(overfetch), pc.n, max_k()))
+        n_splits = auto_splits(pc.op, k_eff, kprime, pc.n) if splits is None else max(1, min(int(splits), pc.n // max(k_eff, 1)))
+        if n_splits > 1:
+            parts_s, parts_i = [], []
+            for v in range(n_splits):
+                sub = _slice_corpus(pc, (pc.n * v) // n_splits, (pc.n * (v + 1)) // n_splits)
+                qd, q_inv, _, cand = topk_candidates(q, sub, k_eff, overfetch, phases=phases)
+                ps, pi = rescore(qd, q_inv, sub, cand, k_eff)
+                parts_s.append(ps)
+                parts_i.append(pi)
+            scores, idx = merge_topk(torch.stack(parts_s), torch.stack(parts_i), k_eff)
+        else:
+            q, q_inv, _, cand = topk_candidates(q, pc, k_eff, overfetch, phases=phases)
+            scores, idx = rescore(q, q_inv, pc, cand, k_eff)
     else:
         q_rows, _ = normalize_cast(q, pc.op, _lib.SIDE_QUERY, pc.metric == "cos", pc.eps)
         scores, idx = topk_prepared_phased(q_rows, n_queries, pc, k_eff, phases) if phases > 1 else \

@@ -57,11 +57,15 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def _cuda_local_topk(queries, shard, k):
+def _cuda_local_topk(queries, shard, k, world: int = 1):
+    """This rank's exact top-k of its shard.  The ranks' shards already act as independent sub-searches (ops.auto_splits), so
+    a shard is split further only as far as the world size leaves the effective over-fetch short."""
     from . import joint, ops
     if isinstance(shard, joint.JointCorpus):
         return joint.topk_joint(queries, shard, k, index_dtype=torch.int32)
-    return ops.topk(queries, shard, k, index_dtype=torch.int32)
+    k_eff = max(1, min(k, shard.n))
+    want = ops.auto_splits(shard.op, k_eff, ops.overfetch_for(k_eff, shard.n), shard.n * world)
+    return ops.topk(queries, shard, k, index_dtype=torch.int32, splits=-(-want // max(1, world)))
 
 
 def _cuda_merge(scores, idx, k):
@@ -145,7 +149,7 @@ class ShardedCorpus:
     """This rank's shard of a row-sharded corpus plus the exchange that merges the ranks' lists."""
 
     def __init__(self, local_rows, n_total: int, start: int, group=None, dtype: str = "bf16", metric: str = "cos",
-                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: str = "global", share_thresholds: bool = True,
+                 eps: float = 1e-12, keep_source: bool = True, exchange: str = "auto", rescore: Optional[str] = None, share_thresholds: bool = True,
                  sub_batches: int = 0, local_topk: Optional[Callable] = None, merge: Optional[Callable] = None,
                  prepare: Optional[Callable] = None, _shard=None):
         self.group = group
@@ -157,9 +161,10 @@ class ShardedCorpus:
         self._min_local = self.n_total // self.world
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
-        if rescore not in ("global", "local"):
-            raise ValueError("rescore must be 'global' or 'local'")
-        self.rescore = rescore
+        if rescore not in (None, "global", "local"):
+            raise ValueError("rescore must be 'global', 'local' or None (auto)")
+        self._rescore_req = rescore
+        self.rescore = rescore or "global"        # auto: settled below, once the shard's operand type is known
         self.share_thresholds = share_thresholds
         self.sub_batches = int(sub_batches)   # 0 = auto
         self.phases = 1                   # single-GPU searches: launches per sweep of the shard (ops.topk_prepared_phased)
@@ -170,7 +175,7 @@ class ShardedCorpus:
         self._peer_failed = False
         self._streams = None
         self._injected = local_topk is not None or merge is not None or prepare is not None
-        self._local_topk = local_topk or _cuda_local_topk
+        self._local_topk = local_topk or (lambda q, shard, k: _cuda_local_topk(q, shard, k, self.world))
         self._merge = merge or _cuda_merge
         if _shard is not None:
             self.shard = _shard
@@ -183,6 +188,12 @@ class ShardedCorpus:
         else:
             self.shard = prepare(local_rows, self.start)
             self.n_local = int(local_rows.shape[0]) if hasattr(local_rows, "shape") else int(local_rows[0].shape[0])
+        if self._rescore_req is None and getattr(self.shard, "op", None) == "fp8" and not self._injected:
+            # e4m3 candidates are lossy: merging the ranks' candidate lists by their fp8 scores down to one K'-list before the
+            # re-score would throw away what the sharding buys (every shard's K' candidates are a `world`-fold over-fetch).
+            # Re-score per shard, exchange exact lists.  (bf16 / fp16 candidates: re-score after the global merge, K'/world rows
+            # per rank -- the sub-millisecond C3 step at 8 GPUs is where that matters.)
+            self.rescore = "local"
 
     # ------------------------------------------------------------------------------------------ constructors
     @classmethod

@@ -162,20 +162,29 @@ def _worker_joint_fp8(rank, world, port, out):
         got = list(sc.topk_stream(iter([[qt, qi], [qt[:50], qi[:50]]]), 10, to_host=True))
         assert torch.equal(got[0][1], i.cpu()) and torch.equal(got[1][1], i[:50].cpu())
 
-        # fp8 shard with fp16 source, top-100: the sharded result equals the unsharded one (same candidate rule)
+        # fp8 shard with fp16 source, top-100.  e4m3 candidates are lossy, so the sharded default is the exact re-score PER
+        # SHARD (every shard's K' candidates survive: a world-fold over-fetch) and the exact lists are merged: the result is
+        # at least as close to the fp32 ranking as the unsharded search of the same rows, and the scores are exact.
         n_rows = 60000
         corpus = torch.randn(n_rows, 768, generator=gen)
         queries = torch.randn(512, 768, generator=gen)
         lo, hi = shard_bounds(n_rows, world, rank)
         shard = m.prepare_streamed(iter([corpus[lo:hi].cuda()]), hi - lo, 768, dtype="fp8", keep_source=torch.float16, idx_offset=lo)
         sc8 = m.ShardedCorpus.from_prepared(shard, n_rows)
+        assert sc8.rescore == "local"
         s8, i8 = sc8.topk(queries.cuda(), 100)
         one = m.prepare_streamed(iter([corpus.cuda()]), n_rows, 768, dtype="fp8", keep_source=torch.float16)
         s1, i1 = m.topk(queries.cuda(), one, 100)
-        assert torch.equal(i8, i1) and torch.equal(s8, s1)
         ref = exact.exact_scores(queries, corpus.half().float())
-        rec = exact.recall_at_k(i8, ref, 100)
-        assert rec >= 0.93, rec                                   # e4m3 candidates, 4 rows of over-fetch at K = 100
+        rec8, rec1 = exact.recall_at_k(i8, ref, 100), exact.recall_at_k(i1, ref, 100)
+        assert rec1 >= 0.93 and rec8 >= 0.985 and rec8 >= rec1, (rec8, rec1)   # 4 rows of over-fetch at K = 100 vs world x 104 candidates
+        assert bool((s8[:, :-1] >= s8[:, 1:]).all())
+        got = torch.gather(ref.cuda(), 1, i8)                                      # returned scores are the exact ones of their rows
+        assert float(((s8.double() - got.double()).abs() / got.double().abs().clamp_min(1e-3)).max()) <= 2e-4
+        # the global-re-score exchange (one K'-list after the candidate merge) still equals the unsharded search bit for bit
+        scg = m.ShardedCorpus.from_prepared(shard, n_rows, rescore="global")
+        sg, ig = scg.topk(queries.cuda(), 100)
+        assert torch.equal(ig, i1) and torch.equal(sg, s1)
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
