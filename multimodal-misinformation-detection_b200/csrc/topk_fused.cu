@@ -45,11 +45,9 @@ namespace {
 constexpr int kTileM = 128;          // queries per tile  (UMMA M, TMEM lanes)
 constexpr int kTileN = 256;          // corpus rows per tile (UMMA N, TMEM columns)
 constexpr int kBlockKBytes = 128;    // one swizzle atom along K per stage
-constexpr int kABytes = kTileM * kBlockKBytes;   // 16 KB of queries per CTA and stage
 // Corpus bytes per CTA and stage: the whole 256-row tile alone (32 KB), or half of it (16 KB) when two
 // CTAs of a pair run one cta_group::2 MMA over 256 queries x 256 corpus rows.
 __host__ __device__ constexpr int b_bytes(int cta) { return (kTileN / cta) * kBlockKBytes; }
-__host__ __device__ constexpr int stage_bytes(int cta) { return kABytes + b_bytes(cta); }
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
@@ -370,11 +368,68 @@ __device__ __forceinline__ uint32_t select_batch(uint64_t* wkeys, const int (&ro
   return failed;
 }
 
+// End of a unit: every row's sorted K'-list, by RANKING, thread <-> row, all 32 rows of the warp at once.  A thread reads
+// only its own row (conflict-free in the [slot][row] layout): it turns its entries into ordered keys in place, then, eight
+// entries at a time, counts how many entries of the row are larger (one shared-memory load per entry of the row, eight
+// independent 64-bit compares per load) and stores each entry straight to its rank in global memory.  n^2 compares per
+// row, but 32 rows in lockstep and no shuffles: ~4x fewer cycles per unit than the warp-cooperative network (which
+// handled one row at a time at ~2 k cycles each, during which the accumulators of the next unit's first tiles wait).
+template <int CAP>
+__device__ __noinline__ RowState final_lists(uint64_t* wkeys, int lane, int kprime, bool valid, int cnt, float thr,
+                                             uint64_t* out, LevelPub pub) {
+  uint64_t* own = wkeys + lane;                         // slot s of this thread's row: own[s * 32]
+  const int n = valid ? cnt : 0;
+  const int nmax = __reduce_max_sync(kFullMask, n);
+#pragma unroll 4
+  for (int i = 0; i < nmax; ++i) {
+    const uint64_t raw = own[i * 32];
+    own[i * 32] = (i < n) ? raw_to_key(raw) : 0ull;     // slots beyond the own count read as empty below
+  }
+  const int last = kprime - 1;
+  int lvl_idx[kMaxLevels];
+#pragma unroll
+  for (int j = 1; j <= kMaxLevels; ++j) lvl_idx[j - 1] = (pub.lvl != nullptr && j <= pub.levels) ? ((kprime + (1 << j) - 1) >> j) - 1 : -1;
+  uint32_t kth = 0u;
+#pragma unroll 1
+  for (int i0 = 0; i0 < nmax; i0 += 8) {
+    uint64_t ki[8];
+    int rank[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      ki[t] = (i0 + t < nmax) ? own[(i0 + t) * 32] : 0ull;
+      rank[t] = 0;
+    }
+#pragma unroll 2
+    for (int j = 0; j < nmax; ++j) {
+      const uint64_t kj = own[j * 32];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) rank[t] += (kj > ki[t]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (ki[t] == 0ull) continue;                       // keys of a row are distinct: its ranks are a permutation
+      if (rank[t] < kprime) out[rank[t]] = ki[t];
+      const uint32_t ord = static_cast<uint32_t>(ki[t] >> 32);
+      if (rank[t] == last) kth = ord;
+#pragma unroll
+      for (int j = 1; j <= kMaxLevels; ++j)              // the score at rank ceil(K' / 2^j), for every level j: see merged bounds
+        if (rank[t] == lvl_idx[j - 1])
+          atomicMax(pub.lvl + static_cast<int64_t>(level_slot0(j) + (pub.strip & ((1 << j) - 1))) * pub.Q + pub.row0 + lane, ord);
+    }
+  }
+  if (valid)
+    for (int i = n; i < kprime; ++i) out[i] = 0ull;      // a short list ends in empty slots
+  RowState st;
+  st.cnt = n < kprime ? n : kprime;
+  st.thr = (n >= kprime) ? fmaxf(thr, ordered_to_float(kth)) : thr;          // never below a bound learnt from other CTAs
+  __syncwarp();
+  return st;
+}
+
 // keep_hi: see select_batch (long lists only; short lists are sorted, which also gives them the exact kprime-th best as bound).
 template <int CAP, bool FINAL>
 __device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int keep_hi, int cnt, float thr,
                                               uint64_t* out_rows, int64_t out_row_stride, LevelPub pub) {
-  constexpr int R = CAP == 64 ? 4 : 2;
   constexpr int E = CAP / 32;
   __syncwarp();
   if constexpr (!FINAL && CAP > 64) {
@@ -391,28 +446,16 @@ __device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, in
     mask = failed;
     __syncwarp();
   }
-  // One instantiation of the network per use (the kernel's rarely executed code runs out of a cold instruction cache:
-  // fewer, reused instructions beat more parallel ones).  End of unit: R rows interleaved, all rows of the warp at once
-  // (a short last batch repeats its last row: same results written twice).  In between: the row that is full, alone.
-  if constexpr (FINAL) {
+  // The kernel's rarely executed code runs out of a cold instruction cache: fewer, reused instructions beat more parallel
+  // ones.  The row that is full goes, alone, through one instantiation of the sorting network (short lists) or of the
+  // selection (long lists); the end of a unit is final_lists().
+  static_assert(!FINAL, "the end of a unit goes through final_lists()");
 #pragma unroll 1
-    while (mask) {
-      int rows[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        rows[r] = mask ? __ffs(mask) - 1 : rows[r > 0 ? r - 1 : 0];
-        mask &= mask - 1;
-      }
-      compact_batch<CAP, FINAL, R, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
-    }
-  } else {
-#pragma unroll 1
-    while (mask) {
-      int rows[1];
-      rows[0] = __ffs(mask) - 1;
-      mask &= mask - 1;
-      compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
-    }
+  while (mask) {
+    int rows[1];
+    rows[0] = __ffs(mask) - 1;
+    mask &= mask - 1;
+    compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
   }
   __syncwarp();
   RowState st;
@@ -443,16 +486,6 @@ __device__ __forceinline__ void thread_sort_desc(float (&v)[N]) {
   }
 }
 
-// Maximum of the 32 scores one tcgen05.ld delivered (3-input maxima on sm_100).
-__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32]) {
-  float m[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
-                 fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
-  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-}
-
 // Bit g set <=> one of columns 4g .. 4g+3 of the 32 loaded scores lies above the row's threshold (NaN never does).
 __device__ __forceinline__ uint32_t group_mask(const uint32_t (&r)[32], float thr) {
   uint32_t m = 0u;
@@ -473,6 +506,9 @@ __device__ __forceinline__ uint32_t group_mask(const uint32_t (&r)[32], float th
 // publication goes to the threshold array of every rank (system-scope atomics over NVLink on peer-mapped memory).
 __device__ __noinline__ void publish_threshold(const FusedParams& p, int64_t qrow, float thr) {
   const uint32_t v = float_to_ordered(thr) - 1u;
+  // most bounds a unit learns are below what is already known (the max over all units and ranks): look before sending --
+  // on a row-sharded corpus a publication is one system-scope atomic per rank over NVLink
+  if (__ldcg(p.thr_global + qrow) >= v) return;
   if (p.n_thr_peers == 0) {
     atomicMax(p.thr_global + qrow, v);
   } else {
@@ -816,23 +852,30 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if constexpr (!kDense) {
         // unit done: emit the sorted K-list of every valid row of this warp
         MMD_ST_T0();
-        const uint32_t vmask = __ballot_sync(kFullMask, valid);
         const int64_t row0 = cta_row0 + quarter * 32;
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
         const float before = thr;
         const LevelPub pub{p.lvl, p.Q, row0, strip, p.levels};
-        const RowState st = compact_rows<CAP, true>(wkeys, vmask, lane, p.kprime, p.keep_hi, cnt, thr, out_rows,
-                                                    static_cast<int64_t>(p.n_strips) * p.kprime, pub);
+        const RowState st = final_lists<CAP>(wkeys, lane, p.kprime, valid, cnt, thr,
+                                             out_rows + static_cast<int64_t>(lane) * p.n_strips * p.kprime, pub);
         cnt = st.cnt;
         thr = st.thr;
         if (valid && thr != before) publish_threshold(p, qrow, thr);
         if (p.lvl != nullptr && valid) {
           // merged bound: fold what the finished strips have left in the quantile slots (this unit's included)
+          // (all loads first: they are independent, and a warp alone on its scheduler pays every L2 round trip in full)
+          uint32_t slot[level_slots(kMaxLevels)];
+          const int n_slots = level_slots(p.levels);
+#pragma unroll
+          for (int s = 0; s < level_slots(kMaxLevels); ++s)
+            slot[s] = s < n_slots ? __ldcg(p.lvl + static_cast<int64_t>(s) * p.Q + qrow) : 0u;
           uint32_t best = 0u;
-          for (int j = 1; j <= p.levels; ++j) {
+#pragma unroll
+          for (int j = 1; j <= kMaxLevels; ++j) {
             uint32_t m = 0xffffffffu;
-            for (int s = 0; s < (1 << j); ++s) m = min(m, __ldcg(p.lvl + static_cast<int64_t>(level_slot0(j) + s) * p.Q + qrow));
-            best = max(best, m);                       // an empty slot (0) voids its level
+#pragma unroll
+            for (int s = 0; s < (1 << j); ++s) m = min(m, slot[level_slot0(j) + s]);
+            best = max(best, m);                       // an empty slot (0) voids its level; so does a level that is off
           }
           if (best != 0u && ordered_to_float(best) > thr) publish_threshold(p, qrow, ordered_to_float(best));
         }
@@ -1237,7 +1280,10 @@ int topk_scores_impl(const void* q_prep, const void* c_prep, int op_dtype, int64
     const int slack = cap - 4 - k;                         // appends a row can take between two compactions (4 per visit)
     p.keep_hi = k + (slack / 8 > 1 ? slack / 8 : 1);
     if (p.keep_hi > cap - 4) p.keep_hi = cap - 4;          // (no slack at all: the selection must be exact)
-    p.early_level = cap - 4 - slack / 4;
+    // (rows that are merely nearly full are NOT taken along: a compaction call of many rows is a burst longer than a tile's
+    //  worth of MMA time, and the issuer then waits for the accumulator -- measured: 8 rows per call = 15.7 k cycles)
+    static const int early = [] { const char* e = getenv("MMD_EARLY"); return e ? atoi(e) : 0; }();   // tuning knob: slack/early rows come along
+    p.early_level = cap - 4 - (early > 0 ? slack / early : 0);
     if (p.early_level < p.keep_hi) p.early_level = p.keep_hi;
     static const int max_levels = [] { const char* e = getenv("MMD_LEVELS"); return e ? atoi(e) : kMaxLevels; }();   // tuning knob (0 = off)
     int levels = 0;

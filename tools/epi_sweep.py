@@ -13,6 +13,7 @@ CASES = {  # name: Q, N, D, k (list length kept by the kernel), kind, op
     "bf16_k100": (16384, 1000000, 768, 100, "text", "bf16"),
     "fp8_k100": (16384, 1000000, 768, 100, "text", "fp8"),
     "fp8_k104_4m": (16384, 4000000, 768, 104, "text", "fp8"),
+    "c3_n8share": (16384, 125000, 768, 18, "text", "bf16"),     # what one of 8 GPUs sees of C3
     "q100": (100, 1000000, 768, 18, "text", "bf16"),
     "q1": (1, 1000000, 768, 18, "text", "bf16"),
 }
