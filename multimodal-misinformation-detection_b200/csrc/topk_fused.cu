@@ -504,16 +504,19 @@ __device__ __forceinline__ uint32_t group_mask(const uint32_t (&r)[32], float th
 // subset of the corpus is a valid lower bound for the K-th best of the whole corpus.
 // With a row-sharded corpus the K-th best of one GPU's shard is equally a lower bound for the global K-th best, so a
 // publication goes to the threshold array of every rank (system-scope atomics over NVLink on peer-mapped memory).
-__device__ __noinline__ void publish_threshold(const FusedParams& p, int64_t qrow, float thr) {
+// `seen` = the largest shared bound of this row the thread has read or written so far: most bounds a unit learns are below
+// what is already known (the max over all units and ranks), and on a row-sharded corpus a publication is one system-scope
+// atomic per rank over NVLink -- those are not sent.  (A register compare: a load here would put an L2 round trip on the
+// path of every compaction of a young row.)
+__device__ __noinline__ uint32_t publish_threshold(const FusedParams& p, int64_t qrow, float thr, uint32_t seen) {
   const uint32_t v = float_to_ordered(thr) - 1u;
-  // most bounds a unit learns are below what is already known (the max over all units and ranks): look before sending --
-  // on a row-sharded corpus a publication is one system-scope atomic per rank over NVLink
-  if (__ldcg(p.thr_global + qrow) >= v) return;
+  if (v <= seen) return seen;
   if (p.n_thr_peers == 0) {
     atomicMax(p.thr_global + qrow, v);
   } else {
     for (int i = 0; i < p.n_thr_peers; ++i) atomicMax_system(p.thr_peer[i] + qrow, v);
   }
+  return v;
 }
 
 // Merged bounds.  thr_global[q] carries the best K'-th best any ONE unit (strip) has seen; the K'-th best of the UNION of
@@ -691,6 +694,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const bool valid = qrow < p.Q;
       float thr = valid ? kNegInf : kPosInf;
       int cnt = 0;
+      uint32_t seen = 0u;                       // largest shared bound of this row read or written by this thread
       MMD_ST_ADD(kStUnits, 1);
       for (int t = t0; t < t1; ++t, ++it) {
         MMD_ST_ADD(kStTiles, 1);
@@ -708,6 +712,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_after();
         if constexpr (!kDense) {
           if (shared_bound != 0u) thr = fmaxf(thr, ordered_to_float(shared_bound));
+          seen = max(seen, shared_bound);
         }
         const int64_t col_tile = static_cast<int64_t>(t) * kTileN;
         const bool edge = col_tile + kTileN > p.N;
@@ -740,7 +745,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int i = 1; i < 32; ++i) kth = (i == p.kprime - 1) ? gmx[i] : kth;
             if (valid && thr == kNegInf && kth > kNegInf) {
-              publish_threshold(p, qrow, kth);
+              seen = publish_threshold(p, qrow, kth, seen);
               thr = ordered_to_float(float_to_ordered(kth) - 1u);     // admit scores equal to the bound
             }
           }
@@ -801,7 +806,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, p.keep_hi, cnt, thr, nullptr, 0, LevelPub{});
               cnt = st.cnt;
               thr = st.thr;
-              if (thr != before) publish_threshold(p, qrow, thr);
+              if (thr != before) seen = publish_threshold(p, qrow, thr, seen);
               MMD_ST_ACC(kStEpiCompact);
             }
             // branch-free appends: raw entry {~column, score bits} stored under a predicate
@@ -860,7 +865,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                                              out_rows + static_cast<int64_t>(lane) * p.n_strips * p.kprime, pub);
         cnt = st.cnt;
         thr = st.thr;
-        if (valid && thr != before) publish_threshold(p, qrow, thr);
+        if (valid && thr != before) seen = publish_threshold(p, qrow, thr, seen);
         if (p.lvl != nullptr && valid) {
           // merged bound: fold what the finished strips have left in the quantile slots (this unit's included)
           // (all loads first: they are independent, and a warp alone on its scheduler pays every L2 round trip in full)
@@ -877,7 +882,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int s = 0; s < (1 << j); ++s) m = min(m, slot[level_slot0(j) + s]);
             best = max(best, m);                       // an empty slot (0) voids its level; so does a level that is off
           }
-          if (best != 0u && ordered_to_float(best) > thr) publish_threshold(p, qrow, ordered_to_float(best));
+          if (best != 0u && ordered_to_float(best) > thr) seen = publish_threshold(p, qrow, ordered_to_float(best), seen);
         }
         MMD_ST_ACC(kStEpiFinal);
       }

@@ -721,6 +721,34 @@ def test_factify_shaped_topk_accuracy_matches_oracle(m):
     assert 0.2 < got[1] < 1.0 and got[10] >= got[1]
 
 
+def test_split_search_raises_effective_overfetch(m):
+    """Long lists / lossy candidates: independent sub-searches (own bounds, own K' candidates, own exact re-score) merged by
+    exact score.  ops.auto_splits picks the count; more splits can only bring the result closer to the fp32 ranking, and
+    the returned scores are always the exact ones of the returned rows (4 spare candidates at k = 100)."""
+    from mmd_retrieval import ops
+    q, c = _data("text", 128, 768, 72), _data("text", 300_000, 768, 73)
+    full = exact.exact_scores(q, c)
+    pc8 = m.prepare_corpus(c.cuda(), dtype="fp8")
+    assert ops.auto_splits("fp8", 100, ops.overfetch_for(100, pc8.n), pc8.n) == 2          # 4 wanted, 2 x 131072 rows fit
+    rec = {}
+    for splits in (1, 2, 4):
+        s, i = m.topk(q.cuda(), pc8, 100, splits=splits)
+        assert tuple(i.shape) == (128, 100) and bool((s[:, :-1] >= s[:, 1:]).all())
+        assert bool((torch.sort(i, dim=1).values.diff(dim=1) > 0).all())                    # no row twice
+        got = torch.gather(full.cuda(), 1, i)
+        assert float(((s.double() - got.double()).abs() / got.double().abs().clamp_min(1e-3)).max()) <= 1e-5
+        rec[splits] = exact.recall_at_k(i, full, 100)
+    s_auto, i_auto = m.topk(q.cuda(), pc8, 100)
+    assert exact.recall_at_k(i_auto, full, 100) == rec[2]
+    assert rec[1] <= rec[2] + 1e-3 and rec[2] <= rec[4] + 1e-3 and rec[4] >= 0.995 and rec[4] > rec[1], rec
+    # bf16, k = 100: two splits make the list exact (one split: K' - k = 4 spare candidates)
+    pc16 = m.prepare_corpus(c.cuda(), dtype="bf16")
+    assert ops.auto_splits("bf16", 100, ops.overfetch_for(100, pc16.n), pc16.n) == 2
+    s, i = m.topk(q.cuda(), pc16, 100)
+    cmp = exact.compare_topk(s, i, full, 100, tie_tol=2e-6)
+    assert cmp.ok and cmp.max_rel_score_err <= 1e-5, cmp
+
+
 def test_fp8_recall(m):
     q, c = _data("text", 256, 768, 70), _data("text", 20000, 768, 71)
     s, i = m.topk(q.cuda(), m.prepare_corpus(c.cuda(), dtype="fp8", keep_source=False), 10, rescore_exact=False)

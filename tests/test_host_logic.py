@@ -135,3 +135,19 @@ def test_compaction_target_leaves_room_for_the_pending_appends():
             t = target(cap, k)
             assert k <= t and (t <= cap - 16 or t == k)
     assert target(64, 18) == 33 and target(128, 104) == 112 and target(128, 120) == 120
+
+
+def test_auto_splits_rule():
+    """ops.auto_splits: sub-searches needed to reach the over-fetch target of the operand type (no GPU involved)."""
+    import importlib
+    ops = importlib.import_module("mmd_retrieval.ops")
+    big = 10_000_000
+    assert ops.auto_splits("bf16", 10, 18, big) == 1            # the default path is untouched
+    assert ops.auto_splits("bf16", 100, 104, big) == 2
+    assert ops.auto_splits("fp16", 100, 104, big) == 2
+    assert ops.auto_splits("fp8", 10, 18, big) == 3
+    assert ops.auto_splits("fp8", 100, 104, big) == 4
+    assert ops.auto_splits("fp32", 100, 100, big) == 1          # exact operands: nothing to recover
+    assert ops.auto_splits("fp8", 100, 104, 300_000) == 2       # never below 131072 rows per split
+    assert ops.auto_splits("fp8", 100, 104, 60_000) == 1
+    assert ops.auto_splits("fp8", 5, 13, big) == 2
