@@ -368,6 +368,48 @@ __device__ __forceinline__ uint32_t select_batch(uint64_t* wkeys, const int (&ro
   return failed;
 }
 
+// End of a unit, a warp with only a few query rows (the reference's one-claim-per-call pattern: ONE row): the rows one at a
+// time, entries spread over the lanes (E per lane), every lane ranks its entries against the whole row (broadcast loads).
+template <int CAP>
+__device__ __forceinline__ void final_row(uint64_t* wkeys, int row, int lane, int kprime, int& cnt, float& thr, uint64_t* out,
+                                          const LevelPub& pub) {
+  constexpr int E = CAP / 32;
+  const int n = __shfl_sync(kFullMask, cnt, row);
+  uint64_t mine[E];
+  int rank[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    mine[e] = (i < n) ? raw_to_key(wkeys[key_slot_index(i, row)]) : 0ull;
+    rank[e] = 0;
+  }
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const uint64_t kj = raw_to_key(wkeys[key_slot_index(j, row)]);       // same address for the whole warp: a broadcast
+#pragma unroll
+    for (int e = 0; e < E; ++e) rank[e] += (kj > mine[e]) ? 1 : 0;
+  }
+  const int last = kprime - 1;
+  uint32_t kth = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (mine[e] == 0ull) continue;
+    if (rank[e] < kprime) out[rank[e]] = mine[e];
+    const uint32_t ord = static_cast<uint32_t>(mine[e] >> 32);
+    if (rank[e] == last) kth = ord;
+    if (pub.lvl != nullptr)
+      for (int j = 1; j <= pub.levels; ++j)
+        if (rank[e] == ((kprime + (1 << j) - 1) >> j) - 1)
+          atomicMax(pub.lvl + static_cast<int64_t>(level_slot0(j) + (pub.strip & ((1 << j) - 1))) * pub.Q + pub.row0 + row, ord);
+  }
+  for (int i = n + lane; i < kprime; i += 32) out[i] = 0ull;               // a short list ends in empty slots
+  kth = __reduce_max_sync(kFullMask, kth);
+  if (lane == row) {
+    cnt = n < kprime ? n : kprime;
+    if (n >= kprime) thr = fmaxf(thr, ordered_to_float(kth));
+  }
+}
+
 // End of a unit: every row's sorted K'-list, by RANKING, thread <-> row, all 32 rows of the warp at once.  A thread reads
 // only its own row (conflict-free in the [slot][row] layout): it turns its entries into ordered keys in place, then, eight
 // entries at a time, counts how many entries of the row are larger (one shared-memory load per entry of the row, eight
@@ -376,7 +418,19 @@ __device__ __forceinline__ uint32_t select_batch(uint64_t* wkeys, const int (&ro
 // handled one row at a time at ~2 k cycles each, during which the accumulators of the next unit's first tiles wait).
 template <int CAP>
 __device__ __noinline__ RowState final_lists(uint64_t* wkeys, int lane, int kprime, bool valid, int cnt, float thr,
-                                             uint64_t* out, LevelPub pub) {
+                                             uint64_t* out, int64_t out_row_stride, LevelPub pub) {
+  uint32_t vmask = __ballot_sync(kFullMask, valid);
+  if (__popc(vmask) <= 6) {
+    // few rows: a lockstep pass over the longest row would be one thread's work at a warp's cost
+#pragma unroll 1
+    while (vmask) {
+      const int row = __ffs(vmask) - 1;
+      vmask &= vmask - 1;
+      final_row<CAP>(wkeys, row, lane, kprime, cnt, thr, out + static_cast<int64_t>(row - lane) * out_row_stride, pub);
+    }
+    __syncwarp();
+    return RowState{cnt, thr};
+  }
   uint64_t* own = wkeys + lane;                         // slot s of this thread's row: own[s * 32]
   const int n = valid ? cnt : 0;
   const int nmax = __reduce_max_sync(kFullMask, n);
@@ -861,8 +915,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         uint64_t* out_rows = p.partial + (row0 * p.n_strips + strip) * p.kprime;
         const float before = thr;
         const LevelPub pub{p.lvl, p.Q, row0, strip, p.levels};
-        const RowState st = final_lists<CAP>(wkeys, lane, p.kprime, valid, cnt, thr,
-                                             out_rows + static_cast<int64_t>(lane) * p.n_strips * p.kprime, pub);
+        const int64_t out_stride = static_cast<int64_t>(p.n_strips) * p.kprime;
+        const RowState st = final_lists<CAP>(wkeys, lane, p.kprime, valid, cnt, thr, out_rows + lane * out_stride, out_stride, pub);
         cnt = st.cnt;
         thr = st.thr;
         if (valid && thr != before) seen = publish_threshold(p, qrow, thr, seen);

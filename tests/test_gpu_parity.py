@@ -566,15 +566,25 @@ def test_text_topk_accuracy_matches_restated_reference_eval(m):
     test_ids = [f"test_{j}".encode() for j in range(n_claims)]
     ss = m.SemanticSimilarity(train.cuda(), train_ids, test.cuda(), test_ids)
     got = m.calculate_topk_accuracy_text_retrieval(ss, claims)
-    lists = []
-    for qi in range(n_claims):
-        res = []
-        for corpus, ids in ((train, train_ids), (test, test_ids)):
-            res += [(ids[h["corpus_id"]].decode(), h["score"]) for h in st_util.semantic_search(claims[qi], corpus, top_k=100)[0]]
-        ranked = sorted(res, key=lambda t: t[1], reverse=True)
-        lists.append([key for key, _ in evalmetrics.dedupe_first_of_each_score(ranked, 10, gold=lambda key, qi=qi: key == f"test_{qi}")])
-    want = evalmetrics.hits_at_k(lists, [f"test_{i}" for i in range(n_claims)], (1, 2, 5, 10))
-    assert got == want, (got, want)
+    # The duplicated rows tie with the gold evidence; which of the two an fp32 pipeline ranks first is decided by the last
+    # bit of two separately computed dot products (the host matmul's blocking depends on the corpus shape and the thread
+    # count).  So the oracle is evaluated with the ties broken both ways (scores rounded to 1e-6, duplicate first / gold
+    # first): the device result must lie between the two, and equal them wherever they agree.
+    bounds = []
+    for gold_first in (False, True):
+        lists = []
+        for qi in range(n_claims):
+            res = []
+            order = ((test, test_ids), (train, train_ids)) if gold_first else ((train, train_ids), (test, test_ids))
+            for corpus, ids in order:
+                res += [(ids[h["corpus_id"]].decode(), round(h["score"], 6)) for h in st_util.semantic_search(claims[qi], corpus, top_k=100)[0]]
+            ranked = sorted(res, key=lambda t: t[1], reverse=True)
+            lists.append([key for key, _ in evalmetrics.dedupe_first_of_each_score(ranked, 10, gold=lambda key, qi=qi: key == f"test_{qi}")])
+        bounds.append(evalmetrics.hits_at_k(lists, [f"test_{i}" for i in range(n_claims)], (1, 2, 5, 10)))
+    lo, hi = bounds
+    for k in (1, 2, 5, 10):
+        assert lo[k] - 1e-9 <= got[k] <= hi[k] + 1e-9, (k, got, lo, hi)
+    assert hi[1] > lo[1]                                             # the ties are there, and the exemption decides them
     assert 0.2 < got[1] <= got[2] <= got[5] <= got[10] <= 1.0
 
 
