@@ -14,7 +14,7 @@ export MMD_NO_AUTOBUILD=1
 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
 echo "pytest rc=$?" | tee -a "$OUT/pytest_gpu.log"
 # the pruning bounds are shared between CTAs as they are learnt (timing dependent): the parity file three more times
-for rep in 1 2 3; do
+for rep in 1 2; do
   python -m pytest tests/test_gpu_parity.py -m gpu -x -q > "$OUT/pytest_parity_rep$rep.log" 2>&1
   echo "parity repeat $rep rc=$?" | tee -a "$OUT/pytest_gpu.log"
 done
@@ -33,12 +33,12 @@ if [ -z "$QUICK" ]; then
     python bench.py --workload $wl --steps $ST --warmup 5 --no-extra > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"
     echo "bench $wl rc=$?"
   done
-  python tools/gpu_diag.py perf2 k1perf > "$OUT/diag_perf.log" 2>&1
+  [ -n "${WITH_DIAG:-}" ] && python tools/gpu_diag.py perf2 k1perf > "$OUT/diag_perf.log" 2>&1
   D=multimodal-misinformation-detection_b200/mmd_retrieval/dev
   SWEEP_TAG="this library" python tools/epi_sweep.py > "$OUT/sweep.log" 2>&1
   [ -f $D/libmmd_r1.so ] && MMD_LIB_PATH=$D/libmmd_r1.so MMD_LIB_PARTIAL=1 SWEEP_TAG="round-1 library" python tools/epi_sweep.py >> "$OUT/sweep.log" 2>&1
   grep sweep "$OUT/sweep.log"
-  if [ -f $D/libmmd_stats.so ]; then
+  if [ -f $D/libmmd_stats.so ] && [ -n "${WITH_COUNTERS:-}" ]; then
     for sh in "c3_k18 16384 1000000 768 18 text bf16" "fp8_k18 16384 1000000 768 18 text fp8" "bf16_k104 16384 1000000 768 104 text bf16" \
               "fp8_k104 16384 1000000 768 104 text fp8" "c2_k18 4096 50000 2048 18 image bf16" "c3_n8share 16384 125000 768 18 text bf16"; do
       set -- $sh; name=$1; shift
@@ -55,12 +55,10 @@ python bench.py $SHORT > "$OUT/plain_c3.log" 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_c3.csv" \
     python bench.py $SHORT > "$OUT/ncu_launches.log" 2>&1
 # full capture of the dominant kernel, C3 shape
-python bench.py $SHORT > "$OUT/plain_c3b.log" 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:fused_score_topk -s 1 -c 2 -f -o "$OUT/prof_c3_fused" \
     python bench.py $SHORT > "$OUT/ncu_c3_fused.log" 2>&1
 if [ -z "$QUICK" ]; then
   # C2 shape
-  python bench.py $SHORT --workload c2 > "$OUT/plain_c2.log" 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:fused_score_topk -s 1 -c 2 -f -o "$OUT/prof_c2_fused" \
       python bench.py $SHORT --workload c2 > "$OUT/ncu_c2_fused.log" 2>&1
   # fp8 instantiations of the fused kernel: CAP = 64 (K' = 18) and CAP = 128 (K' = 100), CTA pairs
@@ -69,8 +67,10 @@ if [ -z "$QUICK" ]; then
         python tools/epi_sweep.py $cs > "$OUT/ncu_${cs}_fused.log" 2>&1
   done
   # K1 (corpus prepare is the first normalize_cast launch) + rescore + merge
-  python bench.py $SHORT > "$OUT/plain_c3c.log" 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"normalize_cast|rescore|merge" -c 6 -f -o "$OUT/prof_c3_aux" \
+  ncu --set full --clock-control none -k regex:"normalize_cast|rescore|merge" -c 5 -f -o "$OUT/prof_c3_aux" \
       python bench.py $SHORT > "$OUT/ncu_c3_aux.log" 2>&1
 fi
-ls -la "$OUT"
+# gpurun brings back at most 64 MiB: summarise the captures here, keep only the C3 capture itself (source page, read offline)
+python tools/make_profiles.py "$OUT" r2 "$OUT/summ" > "$OUT/make_profiles.log" 2>&1
+rm -f "$OUT"/prof_c2_fused.ncu-rep "$OUT"/prof_c3_aux.ncu-rep "$OUT"/prof_fp8_*.ncu-rep
+ls -la "$OUT" "$OUT/summ"

@@ -3,7 +3,7 @@
 profiles/: the launch list, one text summary per .ncu-rep, and traffic.json (dram bytes per fused launch) that
 bench.py reads for roofline.traffic.
 
-    python tools/make_profiles.py gpurun_out/r1a r1
+    python tools/make_profiles.py gpurun_out/r1a r1 [destination directory, default profiles/]
 """
 import csv
 import io
@@ -87,7 +87,7 @@ def launches_table(csv_path, out_md, title):
 
 def main():
     src, rnd = sys.argv[1], sys.argv[2]
-    dst = os.path.join(ROOT, "profiles")
+    dst = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")     # (on the GPU box: a directory under gpurun_out/)
     os.makedirs(dst, exist_ok=True)
     traffic_json = {}
     tpath = os.path.join(dst, "traffic.json")
