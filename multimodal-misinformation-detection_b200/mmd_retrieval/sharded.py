@@ -330,7 +330,7 @@ class ShardedCorpus:
                 for m in mats:
                     m.record_stream(c_stream)
             else:
-                s, i, done = self._run_pipelined(mats, k, ev_up)
+                s, i, done = self._run_pipelined(mats, k, ev_up, overlapped=True)
                 for m in mats:
                     m.record_stream(c_stream)
                     m.record_stream(t_stream)
@@ -469,7 +469,7 @@ class ShardedCorpus:
                                        out=(ring.q_rows[slot], ring.q_inv[slot][0]))
         return rows, [inv]
 
-    def _run_pipelined(self, mats: List[torch.Tensor], k: int, ev_in):
+    def _run_pipelined(self, mats: List[torch.Tensor], k: int, ev_in, overlapped: bool = False):
         """Enqueue one query batch (device matrices, ready on the current stream and -- if given -- at `ev_in`) as pipelined
         sub-steps.  Returns (scores, rows, event that fires when the results are complete).  Nothing here blocks the host."""
         from . import _lib, ops
@@ -486,6 +486,14 @@ class ShardedCorpus:
         op = ops._OP_DTYPE[shard.op]
         # a shard's K'-th best bounds the global K'-th best only if every shard's list is as long as the global candidate list
         share_thr = self.share_thresholds and kp >= kc and self._min_local >= kc
+        # Overlapped batches (topk_stream): the ranks drift apart by up to a batch, a rank's publications then reach peers that
+        # are in another stage, and what remains of the sharing is its cost -- one system-scope atomic per rank and bound over
+        # NVLink.  Measured at 8 GPUs on C3, same box, interleaved (profiles/r2_n8_policy_probe.log): overlapped batches 3.08 ms
+        # with shared thresholds, 2.59 without; one batch at a time 2.69 with, 2.86 without.  At 2 GPUs the stream measured
+        # 9.20 ms with sharing and 9.68 without (different boxes).  So: shared for topk(); for the stream shared up to 4 ranks and
+        # private beyond -- unless the caller asked for sharing explicitly (share_thresholds="always").
+        if overlapped and world > 4 and self.share_thresholds != "always":
+            share_thr = False
         k_loc = max(1, min(kp, shard.n))
         part_stride = ring.q_cap * kp
         sizes = self._sub_sizes(n_queries)

@@ -67,9 +67,13 @@ def _worker_text(rank, world, port, out):
             assert exact.compare_topk(sv, iv, exact.exact_scores(qq, corpus), 10, tie_tol=2e-6).ok, n_q
         # every exchange implementation, stage order, threshold mode and sub-batch split gives the same lists
         for kw in ({"exchange": "nccl"}, {"rescore": "local"}, {"exchange": "nccl", "rescore": "local"}, {"share_thresholds": False},
-                   {"sub_batches": 1}, {"sub_batches": 2}, {"sub_batches": 5}):
+                   {"share_thresholds": "always"}, {"sub_batches": 1}, {"sub_batches": 2}, {"sub_batches": 5}):
             other = m.ShardedCorpus.from_full(corpus.cuda(), **kw)
             s3, i3 = other.topk(queries.cuda(), 10)
+            if kw.get("share_thresholds") == "always":           # overlapped batches WITH cross-GPU bounds (the stream's default is without)
+                for sv, iv in other.topk_stream(iter([queries.cuda(), queries[:77].cuda(), queries.cuda()]), 10):
+                    n = sv.shape[0]
+                    assert torch.equal(iv, i[:n]) and torch.equal(sv, s[:n]), n
             if "exchange" in kw or "rescore" in kw:
                 assert other.exchange == "nccl", (kw, other.exchange)
             cmp3 = exact.compare_topk(s3, i3, full, 10, tie_tol=2e-6)
