@@ -204,66 +204,33 @@ struct LevelPub {
 __host__ __device__ constexpr int level_slot0(int j) { return (1 << j) - 2; }        // first slot of level j >= 1
 __host__ __device__ constexpr int level_slots(int levels) { return (2 << levels) - 2; }
 
-// Sort the candidate buffers of the rows named in `mask` (R of them at a time); keep the best `kprime`.
-//   FINAL = false : write the survivors back.
-//   FINAL = true  : write the sorted list of row r to out_rows + r * out_row_stride (global memory).
-// Returns the calling lane's own (count, threshold): a compacted row holds min(n, kprime) entries and, once it
-// holds kprime, its threshold is at least its kprime-th best score.
-template <int CAP, bool FINAL, int R, int E>
-__device__ __forceinline__ void compact_batch(uint64_t* wkeys, const int (&rows)[R], int lane, int kprime, int& cnt,
-                                              float& thr, uint64_t* out_rows, int64_t out_row_stride, const LevelPub& pub) {
-  // E = registers per lane and row (CAP / 32)
-  uint64_t k[R][E];
-  int n[R];
+// Compaction by sorting (short lists): the row's entries spread over the lanes (E per lane), shuffle bitonic network, the best
+// `kprime` written back in order; the row's threshold becomes its exact kprime-th best -- the tightest filter a row can have.
+template <int CAP>
+__device__ __forceinline__ void sort_row(uint64_t* wkeys, int row, int lane, int kprime, int& cnt, float& thr) {
+  constexpr int E = CAP / 32;
+  uint64_t k[1][E];
+  const int n = __shfl_sync(kFullMask, cnt, row);
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    n[r] = __shfl_sync(kFullMask, cnt, rows[r]);
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int i = e * 32 + lane;
-      k[r][e] = (i < n[r]) ? raw_to_key(wkeys[key_slot_index(i, rows[r])]) : 0ull;
-    }
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    k[0][e] = (i < n) ? raw_to_key(wkeys[key_slot_index(i, row)]) : 0ull;
   }
-  bitonic_sort_desc<E, R>(k, lane);
+  bitonic_sort_desc<E, 1>(k, lane);
+  const int keep = n < kprime ? n : kprime;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < keep) wkeys[key_slot_index(i, row)] = key_to_raw(k[0][e]);
+  }
   const int last = kprime - 1;
+  uint64_t kk = k[0][0];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int keep = n[r] < kprime ? n[r] : kprime;
-    if constexpr (!FINAL) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        if (i < keep) wkeys[key_slot_index(i, rows[r])] = key_to_raw(k[r][e]);
-      }
-    } else {
-      uint64_t* out = out_rows + static_cast<int64_t>(rows[r]) * out_row_stride;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        if (i < kprime) out[i] = k[r][e];   // empty slots are key 0
-      }
-      if (pub.lvl != nullptr) {
-        // the score at rank ceil(K' / 2^j) of this strip's list, for every level j: see merged bounds
-        for (int j = 1; j <= pub.levels; ++j) {
-          const int rank = (kprime + (1 << j) - 1) >> j;
-          const int idx = rank - 1;
-          uint64_t kq = k[r][0];
-#pragma unroll
-          for (int e = 1; e < E; ++e) kq = ((idx >> 5) == e) ? k[r][e] : kq;
-          if (lane == (idx & 31) && n[r] >= rank)
-            atomicMax(pub.lvl + static_cast<int64_t>(level_slot0(j) + (pub.strip & ((1 << j) - 1))) * pub.Q + pub.row0 + rows[r],
-                      static_cast<uint32_t>(kq >> 32));
-        }
-      }
-    }
-    uint64_t kk = k[r][0];
-#pragma unroll
-    for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[r][e] : kk;
-    kk = __shfl_sync(kFullMask, kk, last & 31);
-    if (lane == rows[r]) {
-      cnt = keep;
-      if (n[r] >= kprime) thr = fmaxf(thr, key_score(kk));   // never below a bound learnt from other CTAs
-    }
+  for (int e = 1; e < E; ++e) kk = ((last >> 5) == e) ? k[0][e] : kk;
+  kk = __shfl_sync(kFullMask, kk, last & 31);
+  if (lane == row) {
+    cnt = keep;
+    if (n >= kprime) thr = fmaxf(thr, key_score(kk));   // never below a bound learnt from other CTAs
   }
 }
 
@@ -480,15 +447,15 @@ __device__ __noinline__ RowState final_lists(uint64_t* wkeys, int lane, int kpri
   return st;
 }
 
-// keep_hi: see select_batch (long lists only; short lists are sorted, which also gives them the exact kprime-th best as bound).
-template <int CAP, bool FINAL>
-__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int keep_hi, int cnt, float thr,
-                                              uint64_t* out_rows, int64_t out_row_stride, LevelPub pub) {
-  constexpr int E = CAP / 32;
+// Compaction of the rows named in `mask`, one row at a time in a loop: the rarely executed paths of this kernel run out of a cold
+// instruction cache with one warp per scheduler, and one row's worth of code that the following rows reuse beat the
+// four-rows-interleaved variants by a wide margin (and so did one instantiation of the network instead of four).
+// Short lists are sorted (sort_row); long lists go through the selection (select_batch; keep_hi: see there), rows it
+// cannot split through the sort.  Returns the calling lane's own (count, threshold).
+template <int CAP>
+__device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, int lane, int kprime, int keep_hi, int cnt, float thr) {
   __syncwarp();
-  if constexpr (!FINAL && CAP > 64) {
-    // (one row at a time in a loop: the rarely executed paths of this kernel run out of a cold instruction cache, and one
-    //  row's worth of code that the following rows reuse beat the four-rows-interleaved variant by a wide margin)
+  if constexpr (CAP > 64) {
     uint32_t failed = 0u;
 #pragma unroll 1
     while (mask) {
@@ -500,16 +467,11 @@ __device__ __noinline__ RowState compact_rows(uint64_t* wkeys, uint32_t mask, in
     mask = failed;
     __syncwarp();
   }
-  // The kernel's rarely executed code runs out of a cold instruction cache: fewer, reused instructions beat more parallel
-  // ones.  The row that is full goes, alone, through one instantiation of the sorting network (short lists) or of the
-  // selection (long lists); the end of a unit is final_lists().
-  static_assert(!FINAL, "the end of a unit goes through final_lists()");
 #pragma unroll 1
   while (mask) {
-    int rows[1];
-    rows[0] = __ffs(mask) - 1;
+    const int row = __ffs(mask) - 1;
     mask &= mask - 1;
-    compact_batch<CAP, FINAL, 1, E>(wkeys, rows, lane, kprime, cnt, thr, out_rows, out_row_stride, pub);
+    sort_row<CAP>(wkeys, row, lane, kprime, cnt, thr);
   }
   __syncwarp();
   RowState st;
@@ -857,7 +819,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               MMD_ST_ADD(kStCompCalls, 1);
               MMD_ST_ADD(kStCompRows, __popc(need));
               const float before = thr;
-              const RowState st = compact_rows<CAP, false>(wkeys, need, lane, p.kprime, p.keep_hi, cnt, thr, nullptr, 0, LevelPub{});
+              const RowState st = compact_rows<CAP>(wkeys, need, lane, p.kprime, p.keep_hi, cnt, thr);
               cnt = st.cnt;
               thr = st.thr;
               if (thr != before) seen = publish_threshold(p, qrow, thr, seen);

@@ -34,7 +34,7 @@ if [ -z "$QUICK" ]; then
     echo "bench $wl rc=$?"
   done
   [ -n "${WITH_DIAG:-}" ] && python tools/gpu_diag.py perf2 k1perf > "$OUT/diag_perf.log" 2>&1
-  D=multimodal-misinformation-detection_b200/mmd_retrieval/dev
+  D=${MMD_DEV_LIBS:-multimodal-misinformation-detection_b200/mmd_retrieval/dev}   # developer builds (tools/build_stats.sh; a round-1 libmmd_r1.so for A/B sweeps), shipped to the box only when placed there
   SWEEP_TAG="this library" python tools/epi_sweep.py > "$OUT/sweep.log" 2>&1
   [ -f $D/libmmd_r1.so ] && MMD_LIB_PATH=$D/libmmd_r1.so MMD_LIB_PARTIAL=1 SWEEP_TAG="round-1 library" python tools/epi_sweep.py >> "$OUT/sweep.log" 2>&1
   grep sweep "$OUT/sweep.log"
