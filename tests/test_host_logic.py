@@ -151,3 +151,110 @@ def test_auto_splits_rule():
     assert ops.auto_splits("fp8", 100, 104, 300_000) == 2       # never below 131072 rows per split
     assert ops.auto_splits("fp8", 100, 104, 60_000) == 1
     assert ops.auto_splits("fp8", 5, 13, big) == 2
+
+
+def test_quantile_level_bound_is_a_valid_lower_bound():
+    """The merged bound of the fused kernel (csrc/topk_fused.cu, "Merged bounds"), restated on the host: units publish their
+    score at rank ceil(K'/2^j) into slot (strip mod 2^j) of level j (max per slot); the bound is the max over levels of the min
+    over a level's slots, an empty slot voiding its level.  Whatever subset of strips has finished, in whatever order, and
+    however many equal scores there are, at least K' corpus rows must score at or above the bound."""
+    import random
+    rng = random.Random(7)
+    for trial in range(300):
+        kprime = rng.choice([1, 2, 5, 18, 33, 104, 120])
+        n_strips = rng.randint(1, 40)
+        levels = 0
+        while levels < 4 and (2 << levels) <= n_strips:
+            levels += 1
+        quant = rng.choice([None, 0.05, 0.5])                      # coarse scores: plenty of ties
+        strips = []
+        for _ in range(n_strips):
+            rows = rng.randint(1, 400)
+            sc = [rng.gauss(0.0, 1.0) for _ in range(rows)]
+            if quant:
+                sc = [round(x / quant) * quant for x in sc]
+            strips.append(sorted(sc, reverse=True))
+        slots = {(j, s): None for j in range(1, levels + 1) for s in range(1 << j)}
+        order = list(range(n_strips))
+        rng.shuffle(order)
+        finished = []
+        for strip in order[: rng.randint(1, n_strips)]:
+            finished.append(strip)
+            lst = strips[strip][:kprime]                           # a unit keeps at most K' rows of its strip
+            for j in range(1, levels + 1):
+                rank = -(-kprime // (1 << j))
+                if len(lst) >= rank:
+                    key = (j, strip & ((1 << j) - 1))
+                    slots[key] = lst[rank - 1] if slots[key] is None else max(slots[key], lst[rank - 1])
+            best = None
+            for j in range(1, levels + 1):
+                vals = [slots[(j, s)] for s in range(1 << j)]
+                if all(v is not None for v in vals):
+                    best = min(vals) if best is None else max(best, min(vals))
+            if best is not None:
+                at_or_above = sum(1 for st in finished for x in strips[st] if x >= best)
+                assert at_or_above >= kprime, (trial, kprime, n_strips, levels, best, at_or_above)
+
+
+def _ordered(x: float) -> int:
+    import struct
+    u = struct.unpack("<I", struct.pack("<f", x + 0.0))[0]
+    return (~u) & 0xFFFFFFFF if u & 0x80000000 else u | 0x80000000
+
+
+def _select_bound(ords, kprime, keep_hi):
+    """csrc/topk_fused.cu select_batch, restated: 4-ary search on the order-preserving score word for a bound with between
+    kprime and keep_hi entries above it.  Returns (bound, count) or None when equal scores straddle the kprime-th best."""
+    n = len(ords)
+    lo, hi, c_lo = min(ords) - 1, max(ords), n
+    if n <= keep_hi or n < kprime:
+        return lo, n
+    for _ in range(40):
+        d = hi - lo
+        q = d >> 2
+        t1 = lo + q if q else lo + (d >> 1)
+        t2 = t1 + q if q else t1
+        t3 = t2 + q if q else t1
+        c1, c2, c3 = (sum(1 for o in ords if o > t) for t in (t1, t2, t3))
+        if t1 == lo:
+            return None
+        if c3 >= kprime:
+            lo, c_lo = t3, c3
+        elif c2 >= kprime:
+            lo, c_lo, hi = t2, c2, t3
+        elif c1 >= kprime:
+            lo, c_lo, hi = t1, c1, t2
+        else:
+            hi = t1
+        if c_lo <= keep_hi:
+            return lo, c_lo
+    return None
+
+
+def test_selection_compaction_keeps_the_best_kprime():
+    """The compaction of long lists never drops one of a row's kprime best entries, leaves at most keep_hi, and reports
+    rows it cannot split (ties around the kprime-th best) instead of guessing."""
+    import random
+    rng = random.Random(11)
+    fallbacks = 0
+    for trial in range(400):
+        kprime = rng.choice([33, 64, 100, 104, 120])
+        n = rng.randint(kprime, 127)
+        keep_hi = min(kprime + max(1, (124 - kprime) // 8), 124)
+        quant = rng.choice([None, None, 0.01, 0.2])
+        scores = [rng.gauss(0.1, 0.04) * rng.choice([1.0, 1.0, -1.0]) for _ in range(n)]
+        if quant:
+            scores = [round(x / quant) * quant for x in scores]
+        ords = [_ordered(x) for x in scores]
+        assert all((a < b) == (_ordered(a) < _ordered(b)) for a, b in zip(scores, scores[1:]))      # the mapping preserves order
+        res = _select_bound(ords, kprime, keep_hi)
+        if res is None:
+            fallbacks += 1
+            ranked = sorted(ords, reverse=True)
+            assert ranked[kprime - 1] == ranked[min(keep_hi, n - 1)]            # only a tie run longer than the window fails
+            continue
+        bound, count = res
+        kept = [o for o in ords if o > bound]
+        assert len(kept) == count and (kprime <= count <= keep_hi or count == n <= keep_hi)
+        assert sorted(kept, reverse=True)[:kprime] == sorted(ords, reverse=True)[:kprime]
+    assert fallbacks < 200
