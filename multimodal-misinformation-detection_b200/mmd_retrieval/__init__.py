@@ -11,6 +11,7 @@ Public surface (mirrors the reference's entry points; see DESIGN.md / INTEGRATIO
     SemanticSimilarity                             drop-in for src/evidence/text2text_retrieval.py's search (encoders pluggable)
     ShardedCorpus                                  row-sharded corpus over the GPUs of one box
     prepare_joint / topk_joint                     joint image+text retrieval, weighted score fusion in one contraction
+    BatchedCrossEncoder                            the re-rank stage behind SemanticSimilarity(cross_encoder=...), batched on the GPU
 
 All arithmetic runs in libmmd.so (hand-written sm_100a CUDA behind a C ABI).  There is no CPU fallback.
 """
@@ -24,10 +25,12 @@ from .text_corpus import SemanticSimilarity, calculate_topk_accuracy_text_retrie
 from .sharded import ShardedCorpus, shard_bounds
 from .joint import JointCorpus, prepare_joint, topk_joint
 from .corpus_io import prepare_streamed, load_text_corpus, load_image_corpus
+from .cross_encoder import BatchedCrossEncoder, EncoderConfig
 
 __all__ = [
     "MmdError", "LIB_PATH", "PreparedCorpus", "prepare_corpus", "topk", "dense_scores", "merge_topk", "normalize_cast",
     "max_k", "profile_enable", "profile_collect", "launch_count", "dedupe_by_score", "hits_at_k", "semantic_search",
     "cos_sim", "dot_score", "clear_cache", "ImageCorpus", "ImageSimilarity", "SemanticSimilarity", "calculate_topk_accuracy_text_retrieval", "calculate_topk_accuracy_image_retrieval",
     "ShardedCorpus", "shard_bounds", "JointCorpus", "prepare_joint", "topk_joint", "prepare_streamed", "load_text_corpus", "load_image_corpus",
+    "BatchedCrossEncoder", "EncoderConfig",
 ]

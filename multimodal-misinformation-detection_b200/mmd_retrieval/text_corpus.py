@@ -29,8 +29,10 @@ class SemanticSimilarity:
     train_embeddings / test_embeddings: [N,768] tensors (fp16 in the reference, text2text_retrieval.py:44) or
     PreparedCorpus objects (e.g. from corpus_io.load_text_corpus); *_ids: their row-aligned ids (b"train_17" ...).
     bi_encoder: object with encode(str) -> Tensor[D] (optional: embeddings can be passed to search directly).
-    cross_encoder: callable (query, list_of_texts) -> list of scores, with train_texts / test_texts giving the text of
-    every corpus row (the reference's `evidence_enriched` column); without it the bi-encoder cosine is the final score.
+    cross_encoder: callable (query, list_of_texts) -> list of scores, or an object with a batched predict(list of [query,
+    text] pairs) (mmd_retrieval.cross_encoder.BatchedCrossEncoder; a sentence-transformers CrossEncoder), with train_texts /
+    test_texts giving the text of every corpus row (the reference's `evidence_enriched` column); without it the bi-encoder
+    cosine is the final score.
     """
 
     OVERFETCH = 5     # top_k * 5 per corpus, text2text_retrieval.py:57,62
@@ -70,13 +72,33 @@ class SemanticSimilarity:
         for corpus in (self.train, self.test):
             s, i = ops.topk(emb, corpus, k_each, dense_fallback=True)
             lists.append((s.cpu().tolist(), i.cpu().tolist()))
+        # Re-rank (text2text_retrieval.py:67-95).  A cross-encoder with a batched `predict(pairs)` (mmd_retrieval.cross_encoder.
+        # BatchedCrossEncoder, or a sentence-transformers CrossEncoder) scores the pairs of ALL claims and both corpora in one
+        # call; a plain callable (query, texts) -> scores is called per claim and corpus as the reference does.
+        rerank = self.cross_encoder is not None and query_texts is not None
+        batched_scores = None
+        if rerank and hasattr(self.cross_encoder, "predict"):
+            pairs, where = [], []
+            for ci, ((s_host, i_host), texts) in enumerate(zip(lists, (self.train_texts, self.test_texts))):
+                if texts is None:
+                    continue
+                for qi in range(emb.shape[0]):
+                    for pos, row in enumerate(i_host[qi]):
+                        if row >= 0:
+                            pairs.append((query_texts[qi], texts[row]))
+                            where.append((ci, qi, pos))
+            flat = self.cross_encoder.predict(pairs) if pairs else []
+            batched_scores = {w: float(c) for w, c in zip(where, flat)}
         out = []
         for qi in range(emb.shape[0]):
             results: List[Tuple[str, float]] = []
-            for (s_host, i_host), ids, texts in zip(lists, (self.train_ids, self.test_ids), (self.train_texts, self.test_texts)):
+            for ci, ((s_host, i_host), ids, texts) in enumerate(zip(lists, (self.train_ids, self.test_ids), (self.train_texts, self.test_texts))):
                 hits = [(row, score) for score, row in zip(s_host[qi], i_host[qi]) if row >= 0]
-                if self.cross_encoder is not None and texts is not None and query_texts is not None:
-                    cross = self.cross_encoder(query_texts[qi], [texts[row] for row, _ in hits])
+                if rerank and texts is not None:
+                    if batched_scores is not None:
+                        cross = [batched_scores[(ci, qi, pos)] for pos, row in enumerate(i_host[qi]) if row >= 0]
+                    else:
+                        cross = self.cross_encoder(query_texts[qi], [texts[row] for row, _ in hits])
                     hits = sorted(((row, float(c)) for (row, _), c in zip(hits, cross)), key=lambda t: t[1], reverse=True)[:k_each]
                 results += [(_decode(ids[row]), score) for row, score in hits]
             ranked = sorted(results, key=lambda t: t[1], reverse=True)
