@@ -97,7 +97,9 @@ MMD_API int mmd_normalize_cast_segment(const void* src, int src_dtype, int64_t r
 /* ---- K2+K3: tensor-core score contraction with fused top-K ---------------------------------- */
 /* Largest K the fused selection supports. */
 MMD_API int mmd_topk_max_k(void);
-/* Bytes of scratch mmd_topk_scores needs for this problem. */
+/* Bytes of scratch mmd_topk_scores needs for this problem: one K-list of 64-bit keys per (query, strip of the planned
+ * schedule), the per-query pruning bounds (uint32 [Q]) and the quantile slots of the merged bounds (uint32 [30][Q]).  Device
+ * memory, 8-byte aligned, private to one call in flight; the library zeroes what it reads. */
 MMD_API size_t mmd_topk_workspace_bytes(int64_t Q, int64_t N, int dim, int op_dtype, int k);
 
 /* q_prep [Q rows], c_prep [N rows]: prepared by mmd_normalize_cast with the same op_dtype / dim.
