@@ -12,11 +12,13 @@
 //   warp 0 (one lane)  TMA producer: {128 queries x 128 B} and {256 corpus rows x 128 B} boxes, 128B swizzle,
 //                      multi-stage ring of mbarriers.
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma 128x256x(32 B) into one of two 256-column TMEM accumulators.
-//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> query row.  Per tile a branch-free
-//                      FILTER pass (chunk maxima against the row thresholds, TMEM loads software pipelined) marks the
-//                      chunks worth a second look; a COLLECT pass re-reads only those and appends scores above the
-//                      row's threshold to a per-row candidate buffer in shared memory (predicated stores), which
-//                      the warp compacts with a shuffle bitonic sort when it fills.
+//   warps 2..5         epilogue: thread <-> query row.  Per tile a branch-free FILTER pass (tcgen05.ld 32 lanes x 32 columns,
+//                      two loads in flight; the maxima of the tile's 64 groups of 4 columns against the row thresholds,
+//                      OR-ed over the warp) names the groups worth a second look; a COLLECT pass re-reads only those
+//                      (tcgen05.ld .x4) and appends scores above the row's threshold to a per-row candidate buffer in
+//                      shared memory (predicated stores).  A full row is compacted alone: short lists by a shuffle bitonic
+//                      sort, long lists by a 4-ary selection on the score word.  At the end of a unit every thread ranks
+//                      its own row and stores the sorted K-list.
 // Work decomposition: unit = (128-query tile, strip of T corpus tiles), query tile fastest so that the
 // CTAs running at the same time read the same corpus rows (L2 reuse; HBM sees the corpus ~once).
 // Every unit leaves a sorted K-list per query; topk_merge.cu folds the strips together.
